@@ -1,0 +1,324 @@
+#!/usr/bin/env python
+"""bench.py -- HW1F path-steps/s on the BASELINE.json headline workload.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one pass of the hot path over one batch: the Q1 bond-curve workload of
+BASELINE.json (`configs[0]`, the configuration the metric is quoted on): 2^20 RNG subsequences x 2
+antithetic paths x 1000 exact-discretisation steps per GPU, stateless XORWOW seeding included,
+deterministic two-level reduction to 202 double moments.  With N > 1 every rank simulates its own
+disjoint subsequence range (weak scaling) and the moment vectors are combined with ONE NCCL
+all-reduce of 202 doubles per step.
+
+`value`  : device-timed (CUDA events on the launching stream), nothing crosses PCIe in the region.
+`e2e`    : the public host-buffer call a user makes (set_model H2D + simulate + finalise + D2H of
+           P, f, P_se), wall-clock between synchronisations.
+`roofline`: this path is instruction-issue / FP32+XU pipe bound, not HBM or tensor:
+           achieved = algorithmic pipe instructions/s (12 issue slots per path-step), peak = the
+           issue rate measured by the engine's own pipe probes on this GPU at the clock seen.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "tests")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+METRIC = "HW1F path-steps/s (2M antithetic paths, 1000 steps)"
+UNIT = "path-steps/s"
+N_PATHS_LOG2 = 20          # reference N_PATHS = 1024*1024 (include/common.cuh:16)
+ALGO_ISSUE_PER_PATHSTEP = 12.0   # 6.75 FP32 + 1.0 MUFU + 3.75 INT + 0.5 I2F
+ALGO_FP32_PER_PATHSTEP = 6.75
+ALGO_XU_PER_PATHSTEP = 1.0
+
+
+class ClockSampler(threading.Thread):
+    """samples SM clock / throttle reasons with NVML while the timed regions run"""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self._stop = index, [], threading.Event()
+        self.max_mhz, self.ok = None, False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                mhz = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(
+                    nv, "nvmlDeviceGetCurrentClocksEventReasons") else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                power = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                self.samples.append((time.time(), mhz, reasons, power))
+            except Exception:
+                pass
+            time.sleep(0.01)
+
+    def stop(self):
+        self._stop.set()
+
+    def summary(self, t0, t1):
+        sel = [s for s in self.samples if t0 <= s[0] <= t1] or self.samples
+        if not sel:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
+        names = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+                 0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+                 0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+        bits = 0
+        for s in sel:
+            bits |= s[2]
+        reasons = [n for b, n in names.items() if bits & b and n != "gpu_idle"]
+        return {"sm_mhz": statistics.median(s[1] for s in sel), "sm_max_mhz": self.max_mhz, "reasons": reasons,
+                "power_w_max": max(s[3] for s in sel), "samples": len(sel)}
+
+
+def run_reference_arm(args, rank):
+    """the reference's own CUDA implementation of the path (the reference has no CPU path), driven
+    by oracle/_ref/ref_harness on GPU 0; falls back to the OpenMP oracle port if it was not built"""
+    if rank != 0:
+        return
+    harness = os.path.join(ROOT, "oracle", "_ref", "ref_harness")
+    n_paths = 1 << N_PATHS_LOG2
+    line = {"metric": METRIC, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "Q1 bond curve: 2^20 subsequences x 2 antithetic x 1000 steps (reference "
+                                   "simulate_zcb), seeds pinned"}}
+    if os.path.exists(harness):
+        out = os.path.join(ROOT, "gpurun_out", "ref_bench_q1.json")
+        os.makedirs(os.path.dirname(out), exist_ok=True)
+        env = dict(os.environ, CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", "0").split(",")[0])
+        subprocess.run([harness, "bench", "q1", str(args.steps), str(args.warmup), out], check=True, env=env,
+                       stdout=subprocess.DEVNULL, timeout=1800)
+        with open(out) as f:
+            r = json.load(f)
+        ms = r["workload_ms_per_step"]
+        value = r["path_steps_per_step"] / (ms * 1e-3)
+        line.update({"value": value, "ms_per_step": ms, "gpu_launches": 3 * args.steps,
+                     "kernel_only": {"value": r["path_steps_per_step"] / (r["kernel_ms_per_step"] * 1e-3),
+                                     "ms_per_step": r["kernel_ms_per_step"],
+                                     "note": "simulate_zcb alone: the reference's own published metric "
+                                             "(src/1_bond_pricing.cu:64-71), init_rng excluded"},
+                     "init_rng_ms_per_step": r["init_rng_ms_per_step"],
+                     "cpu_baseline": {"value": value, "unit": UNIT, "cores": 0, "kind": "reference",
+                                      "sample": "unmodified reference kernels rebuilt for sm_100 (CUDA-only reference, "
+                                                "no CPU path): init_rng + simulate_zcb + compute_average_and_forward "
+                                                "+ D2H per step on the same B200, CUDA-event timed"},
+                     "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+    else:
+        from oracle_lib import Oracle
+        o = Oracle()
+        n = 1 << 14
+        t0 = time.time()
+        for _ in range(max(args.steps, 1)):
+            o.bond_curve(1234, n)
+        dt = (time.time() - t0) / max(args.steps, 1)
+        value = 2.0 * n * 1000 / dt
+        line.update({"value": value, "ms_per_step": dt * 1e3, "gpu_launches": 0,
+                     "cpu_baseline": {"value": value, "unit": UNIT, "cores": o.max_threads(), "kind": "port",
+                                      "sample": "OpenMP oracle, 2^14 pairs x 1000 steps per step"},
+                     "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
+    ap.add_argument("--paths-log2", type=int, default=N_PATHS_LOG2, help="subsequences per GPU (default 2^20)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference_arm(args, rank)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import hw1f_b200 as hw
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the HW1F engine has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # a dedicated non-default stream: the engine launches on it, torch events / NCCL see it
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    eng = hw.Engine(device=local_rank, stream=stream.cuda_stream)
+    n_paths = 1 << args.paths_log2
+    n_steps, n_mat = eng.n_steps, eng.n_mat
+    first_path = rank * n_paths                       # disjoint XORWOW subsequence ranges per rank
+    path_steps_per_step = 2.0 * n_paths * n_steps * world
+    moments = torch.zeros(2 * n_mat, dtype=torch.float64, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    def device_step(seed):
+        rng = hw.Rng(seed, n_paths, first_path=first_path)
+        eng.bond_curve_moments(rng, moments.data_ptr())
+        if world > 1:
+            dist.all_reduce(moments)                 # the single collective of the path: 202 doubles
+
+    def e2e_step(seed):
+        eng.set_model(eng.params)                    # compute_constants(): H2D of the model tables
+        rng = hw.Rng(seed, n_paths, first_path=first_path)
+        eng.bond_curve_moments(rng, moments.data_ptr())
+        if world > 1:
+            dist.all_reduce(moments)
+        return eng.bond_curve_finish(moments.data_ptr(), n_paths * world)   # D2H of P, f, P_se
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+
+    # ---- warm-up (also builds the jump tables once; they are seed independent) ----
+    for i in range(args.warmup):
+        device_step(1000 + i)
+        flush.zero_()
+    barrier()
+
+    # ---- device-timed region: per-step event pairs, L2 flushed between steps ----
+    launches0 = eng.launch_count
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    t_load0 = time.time()
+    for i in range(args.steps):
+        ev[i][0].record()
+        device_step(5000 + i)
+        ev[i][1].record()
+        flush.zero_()
+    barrier()
+    t_load1 = time.time()
+    launches = eng.launch_count - launches0
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    ms_per_step = float(total_ms.item()) / args.steps
+    value = path_steps_per_step / (ms_per_step * 1e-3)
+
+    # ---- end-to-end region: public host-buffer API, wall clock between synchronisations ----
+    for i in range(3):
+        e2e_step(9000 + i)
+    barrier()
+    t0 = time.time()
+    for i in range(args.steps):
+        last = e2e_step(7000 + i)
+    barrier()
+    e2e_s = torch.tensor([time.time() - t0], dtype=torch.float64, device=dev)
+    t_load2 = time.time()
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_ms = float(e2e_s.item()) * 1e3 / args.steps
+    e2e_value = path_steps_per_step / (e2e_ms * 1e-3)
+    sampler.stop()
+    clocks = sampler.summary(t_load0, t_load2)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline denominators measured here: issue rate and pipe rates of this GPU ----
+    def rate(which, iters=512):
+        ms, n = eng.pipe_probe(which, iters)
+        return n / (ms * 1e-3)
+    ffma, ffma2, mufu, alu, i2f, mix = rate(0), rate(1), rate(2), rate(3), rate(4, 128), rate(6, 128)
+    sm_mhz = clocks.get("sm_mhz") or 1965.0
+    sm_count = torch.cuda.get_device_properties(local_rank).multi_processor_count
+    issue_peak_nominal = sm_count * 4 * 32 * sm_mhz * 1e6        # lane-instructions/s at the clock seen
+    issue_peak = max(ffma, alu, mix)                              # measured: best single-issue stream
+    per_gpu = value / world
+    achieved = per_gpu * ALGO_ISSUE_PER_PATHSTEP
+    roofline = {
+        "bound": "issue", "achieved": achieved / 1e9, "peak": issue_peak / 1e9, "unit": "Ginstr/s (thread-level)",
+        "frac": achieved / issue_peak, "traffic": None,
+        "peak_source": "measured by hw1f_pipe_probe on this GPU in this run (FFMA / LOP3 / mixed streams); "
+                       "MEASURED_PEAKS.json has no FP32/XU entry (HBM and bf16 tensor only)",
+        "issue_peak_nominal_at_clock": issue_peak_nominal / 1e9,
+        "fp32_pipe": {"achieved": per_gpu * ALGO_FP32_PER_PATHSTEP / 1e9, "peak_ffma": ffma / 1e9,
+                      "peak_ffma2_lanes": 2 * ffma2 / 1e9,
+                      "frac": per_gpu * ALGO_FP32_PER_PATHSTEP / max(ffma, 2 * ffma2)},
+        "xu_pipe": {"achieved": per_gpu * ALGO_XU_PER_PATHSTEP / 1e9, "peak_mufu": mufu / 1e9,
+                    "frac": per_gpu * ALGO_XU_PER_PATHSTEP / mufu},
+        "probes_Ginstr_s": {"ffma": ffma / 1e9, "ffma2": ffma2 / 1e9, "mufu_ex2": mufu / 1e9, "lop3_shf": alu / 1e9,
+                            "i2fp": i2f / 1e9, "hw1f_mix": mix / 1e9},
+        "algorithmic_per_path_step": {"issue": ALGO_ISSUE_PER_PATHSTEP, "fp32": ALGO_FP32_PER_PATHSTEP,
+                                      "xu": ALGO_XU_PER_PATHSTEP},
+        "kernel": "bond_curve_kernel<true,1> (prep_lo_kernel + reduce_partials_kernel included in the time)",
+    }
+
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle_lib import Oracle
+        o = Oracle()
+        n_cpu = 1 << 16                                # BASELINE.json configs[0]: oracle at 2^16 paths
+        o.bond_curve(1, 1 << 10)
+        t0 = time.time()
+        o.bond_curve(1234, n_cpu)
+        dt = time.time() - t0
+        cpu_baseline = {"value": 2.0 * n_cpu * n_steps / dt, "unit": UNIT, "cores": o.max_threads(), "kind": "port",
+                        "sample": f"OpenMP C oracle (oracle/hw1f_oracle.c), Q1 at 2^16 subsequences x 2 x 1000 steps, "
+                                  f"{dt:.2f} s wall"}
+
+    bad = {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"} & set(clocks.get("reasons", []))
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"Q1 bond curve P(0,T), f(0,T): 2^{args.paths_log2} XORWOW subsequences x 2 antithetic "
+                               f"paths x {n_steps} steps per GPU, r0=0.012 a=1 sigma=0.1, {n_mat} maturities, "
+                               "seeding included",
+                   "paths_per_gpu": 2 * n_paths, "n_steps": n_steps, "l2": "flushed between steps (256 MiB memset, "
+                   "outside the per-step event pairs)", "parallelism": f"path-range sharding x{world}, one NCCL "
+                   "all-reduce of 202 doubles per step" if world > 1 else "single GPU"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms,
+                "h2d_bytes_per_step": 2 * (n_steps + 2) * 8, "d2h_bytes_per_step": 3 * n_mat * 4},
+        "gpu_launches": int(launches),
+        "clocks": clocks, "clock_check": "rejected: thermal/hw slowdown seen" if bad else "ok",
+        "roofline": roofline,
+        "cpu_baseline": cpu_baseline,
+        "check": {"P_0_10": float(last["P"][-1]), "f_0_0": float(last["f"][0])},
+        "published_v100_path_steps_per_s": 3.91e11,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

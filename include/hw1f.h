@@ -1,0 +1,238 @@
+/*
+ * include/hw1f.h -- C ABI of the B200-native Hull-White one-factor Monte Carlo engine.
+ *
+ * The reference (giulialionetti/Monte-Carlo-simulation-of-Hull-White-model-and-
+ * sensitivities-computation) has no FFI: its "operator surface" is the set of
+ * kernel launches, __constant__-symbol writes and raw device buffers that its four
+ * drivers perform in the same translation unit as main().  Every entry point below
+ * names the reference call sites it replaces (paths relative to the reference root).
+ *
+ * Conventions
+ *   - plain C types only; all array arguments are HOST pointers unless the name
+ *     starts with d_ (device pointer, used by the *_moments / *_finish pairs that
+ *     let a caller put its own collective between simulation and finalisation);
+ *   - every function returns an int status (HW1F_OK == 0); nothing calls exit()
+ *     (the reference's check_cuda() does, include/common.cuh:114-120);
+ *   - "n_paths" is the reference's N_PATHS: the number of RNG subsequences.  The
+ *     antithetic kernels simulate 2*n_paths trajectories, like the reference;
+ *   - RNG streams are cuRAND-XORWOW compatible: path p of an hw1f_rng created with
+ *     (seed, first_path) sees exactly the Gaussians that
+ *     curand_init(seed, first_path + p, 0, &st) + curand_normal(&st) would deliver
+ *     (include/common.cuh:277-280, :327), starting at the handle's normal offset.
+ *     No per-path state array exists; the state is re-derived inside the kernels.
+ *   - there is NO CPU fallback: without a CUDA device every compute call fails.
+ */
+#ifndef HW1F_H
+#define HW1F_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HW1F_OK 0
+#define HW1F_ERR_INVALID 1        /* bad argument                          */
+#define HW1F_ERR_CUDA 2           /* a CUDA runtime call failed             */
+#define HW1F_ERR_NO_DEVICE 3      /* no usable CUDA device                  */
+#define HW1F_ERR_UNSUPPORTED 4    /* configuration outside the engine       */
+#define HW1F_ERR_NO_MODEL 5       /* hw1f_set_model() not called yet        */
+
+#define HW1F_ABI_VERSION 1
+
+/* ---- model ------------------------------------------------------------------ */
+/* Replaces the compile-time configuration of include/common.cuh:16-39 and the
+ * piecewise-linear theta hard-coded at common.cuh:74-76 / :228-230. */
+typedef struct hw1f_params {
+    float a;            /* H_A      mean reversion                */
+    float sigma;        /* H_SIGMA  volatility                    */
+    float r0;           /* H_R0     initial short rate            */
+    float T_final;      /* T_FINAL                                */
+    int32_t n_steps;    /* N_STEPS                                */
+    int32_t n_mat;      /* N_MAT    (n_steps % (n_mat-1) == 0)    */
+    float theta_a0, theta_b0;   /* theta(t) = a0 + b0 t, t <  theta_break */
+    float theta_a1, theta_b1;   /* theta(t) = a1 + b1 t, t >= theta_break */
+    float theta_break;
+    float fd_theta_a1;  /* constant used by compute_shifted_drift_table for t >= break
+                           (0.014 in src/3_sensitivity_analysis.cu:387; quirk kept) */
+} hw1f_params;
+
+typedef struct hw1f_engine hw1f_engine; /* one per (process, device): tables, scratch, stream */
+typedef struct hw1f_rng hw1f_rng;       /* (seed, first_path, n_paths, normal offset)        */
+
+int hw1f_abi_version(void);
+const char* hw1f_status_string(int status);
+/* message of the last failure on this engine (never NULL) */
+const char* hw1f_last_error(const hw1f_engine* eng);
+
+/* select_gpu() + cudaMalloc of every scratch buffer (common.cuh:122-141; src/1:38-42).
+ * device < 0 picks the device with the most free memory like select_gpu(). */
+int hw1f_engine_create(int device, hw1f_engine** out);
+int hw1f_engine_destroy(hw1f_engine* eng);
+/* run on a caller-owned cudaStream_t (NULL = the engine's own stream) */
+int hw1f_engine_set_stream(hw1f_engine* eng, void* cuda_stream);
+int hw1f_engine_device(const hw1f_engine* eng, int* device);
+int hw1f_engine_synchronize(hw1f_engine* eng);
+
+/* H_* constants of common.cuh:33-39 */
+int hw1f_default_params(hw1f_params* out);
+/* compute_constants() + compute_drift_tables(): every cudaMemcpyToSymbol of
+ * common.cuh:82-83,98-106 and src/3:416-420,428-432,439-441,453-455,518-520. */
+int hw1f_set_model(hw1f_engine* eng, const hw1f_params* p);
+int hw1f_get_model(const hw1f_engine* eng, hw1f_params* out);
+/* host copies of the derived constants, for callers that print them */
+typedef struct hw1f_constants {
+    float dt, mat_spacing, exp_adt, sig_st;
+    int32_t save_stride;
+} hw1f_constants;
+int hw1f_get_constants(const hw1f_engine* eng, hw1f_constants* out);
+/* which = 0: drift table at sigma (common.cuh:73-76); 1: sensitivity drift table (common.cuh:79-80);
+ * 2: shifted drift table for sigma vs. the model sigma (src/3:374-398).  out[n_steps]. */
+int hw1f_get_drift_table(const hw1f_engine* eng, int which, float sigma, float* out);
+/* (int)(S1 / d_dt) exactly as the reference's fast-math build evaluates it on this GPU
+ * (MUFU.RCP(d_dt)*S1 then F2I.TRUNC; common.cuh:322, src/3:46). */
+int hw1f_steps_to(hw1f_engine* eng, float S1, int32_t* n_steps_S1);
+
+/* ---- RNG handle ---------------------------------------------------------------- */
+/* cudaMalloc(states) + init_rng<<<NB,NTPB>>>(states, seed)
+ * (src/1:41,53; src/2:120,128,227,230; src/3:543,547,712,713; src/bench:94,95). */
+int hw1f_rng_create(uint64_t seed, uint64_t first_path, uint64_t n_paths, hw1f_rng** out);
+/* the state-array backup of src/3:407-409,494-497 (D2D copy of 48 B/path there) */
+int hw1f_rng_clone(const hw1f_rng* src, hw1f_rng** out);
+int hw1f_rng_destroy(hw1f_rng* rng);
+/* number of normals every path has consumed so far (the reference keeps this implicitly
+ * in the written-back curandState) */
+int hw1f_rng_tell(const hw1f_rng* rng, uint64_t* normal_offset);
+/* the state restore of src/3:422,434,502,509 */
+int hw1f_rng_seek(hw1f_rng* rng, uint64_t normal_offset);
+int hw1f_rng_info(const hw1f_rng* rng, uint64_t* seed, uint64_t* first_path, uint64_t* n_paths);
+
+/* ---- Q1: zero-coupon curve -------------------------------------------------------- */
+/* simulate_zcb<<<NB,NTPB>>> + compute_average_and_forward<<<1,128>>>
+ * (include/market_data.cuh:25-127; src/1:65,75; src/3:471,474).
+ * P[n_mat], f[n_mat]; P_se[n_mat] (standard error of P from the pair-sample variance; may be
+ * NULL); sim_ms (CUDA-event time of the simulation, may be NULL).  Advances rng by n_steps. */
+int hw1f_bond_curve(hw1f_engine* eng, hw1f_rng* rng, float* P, float* f, float* P_se, float* sim_ms);
+/* split form: d_moments[2*n_mat] doubles on the device = {sum_m p0_m, sum_m p0_m^2} over this
+ * handle's paths (entry 0 unused).  A caller may all-reduce d_moments across ranks before
+ * calling hw1f_bond_curve_finish with the global path count. */
+int hw1f_bond_curve_moments(hw1f_engine* eng, hw1f_rng* rng, double* d_moments);
+int hw1f_bond_curve_finish(hw1f_engine* eng, const double* d_moments, uint64_t n_paths_total,
+                           float* P, float* f, float* P_se);
+
+/* ---- Q2a: theta calibration --------------------------------------------------------- */
+/* recover_theta<<<1,N_MAT>>> (src/2_option_pricing.cu:14-35,82). All arrays [n_mat]. */
+int hw1f_theta_calibrate(hw1f_engine* eng, const float* f, float* theta_rec, float* theta_ref, float* T);
+
+/* ---- Q2b: ZBC with optimal-beta control variate ------------------------------------- */
+typedef struct hw1f_zbc_result {
+    double mom[5];          /* sum X, sum Y, sum X^2, sum Y^2, sum XY (per-thread pair sums, as the
+                               reference accumulates them: common.cuh:356-362)          */
+    uint64_t n_total;       /* 2 * n_paths                                             */
+    int32_t n_steps_S1;
+    int32_t reserved;
+    /* float32 host algebra of src/2:154-179 and src/2:259-290, same operation order */
+    float mean_X, mean_Y, var_X, var_Y, cov, beta, control_adjustment;
+    float price_raw;        /* mean_X                                                  */
+    float price_cv;         /* mean_X - beta (mean_Y - P0S2)                           */
+    float corr_single;      /* "Correlation" of src/2:178 (algebraically beta)         */
+    float corr;             /* rho of src/2:281                                        */
+    /* additions (double algebra on the double moments) */
+    double price_cv_f64, beta_f64, se_raw, se_cv, ci95_lo, ci95_hi;
+} hw1f_zbc_result;
+
+/* simulate_ZBC_control_variate<<<NB,NTPB>>> + host algebra (common.cuh:286-409; src/2:136,246;
+ * src/3:127).  P_mkt/f_mkt[n_mat] as loaded from data/P.bin, data/f.bin.  n_steps_S1 < 0 derives
+ * it with hw1f_steps_to.  Advances rng by n_steps_S1.  (Bumped-sigma pricing, i.e. what
+ * run_finite_difference does around run_zbc_price, is hw1f_vega_fd below.) */
+int hw1f_zbc_cv(hw1f_engine* eng, hw1f_rng* rng, float S1, float S2, float K,
+                const float* P_mkt, const float* f_mkt, int32_t n_steps_S1,
+                hw1f_zbc_result* out, float* sim_ms);
+int hw1f_zbc_cv_moments(hw1f_engine* eng, hw1f_rng* rng, float S1, float S2, float K,
+                        const float* P_mkt, const float* f_mkt, int32_t n_steps_S1, double* d_moments);
+int hw1f_zbc_cv_finish(hw1f_engine* eng, const double* d_moments, uint64_t n_paths_total, float P0S2,
+                       hw1f_zbc_result* out);
+/* the 20-run validation of src/2:210-302 as ONE launch with a seed axis: seeds[n_runs] */
+int hw1f_zbc_cv_batch(hw1f_engine* eng, const uint64_t* seeds, int32_t n_runs, uint64_t n_paths,
+                      float S1, float S2, float K, const float* P_mkt, const float* f_mkt,
+                      int32_t n_steps_S1, hw1f_zbc_result* out, float* sim_ms);
+
+/* ---- Q3: vega ------------------------------------------------------------------------ */
+typedef struct hw1f_vega_result {
+    /* pathwise (simulate_sensitivity, src/3:22-96,251): sum / n_paths like src/3:261 */
+    float vega_pathwise; double vega_pathwise_f64, vega_pathwise_se;
+    /* finite differences with common random numbers (src/3:400-446) */
+    float price_minus, price_plus, vega_fd;
+    /* recalibrated FD (src/3:449-525) */
+    float price_minus_recal, price_plus_recal, vega_fd_recal;
+    int32_t n_steps_S1;
+    float ms_pathwise, ms_fd, ms_fd_recal;
+} hw1f_vega_result;
+
+int hw1f_vega_pathwise(hw1f_engine* eng, hw1f_rng* rng, float S1, float S2, float K,
+                       const float* P_mkt, const float* f_mkt, int32_t n_steps_S1,
+                       hw1f_vega_result* out);
+/* d_moments[2] = {sum v, sum v^2} */
+int hw1f_vega_pathwise_moments(hw1f_engine* eng, hw1f_rng* rng, float S1, float S2, float K,
+                               const float* P_mkt, const float* f_mkt, int32_t n_steps_S1, double* d_moments);
+/* both bumps in ONE launch on the same normals (the reference restores a 50 MB state backup
+ * between two launches, src/3:407-435).  Advances rng by n_steps_S1. */
+int hw1f_vega_fd(hw1f_engine* eng, hw1f_rng* rng, float S1, float S2, float K,
+                 const float* P_mkt, const float* f_mkt, float eps, int32_t n_steps_S1,
+                 hw1f_vega_result* out);
+/* recompute_market_data at sigma -/+ eps (both curves in one launch) then the two prices; the
+ * handle is left where the reference leaves its state array (advanced by n_steps_S1). */
+int hw1f_vega_fd_recalibrated(hw1f_engine* eng, hw1f_rng* rng, float S1, float S2, float K,
+                              float eps, int32_t n_steps_S1, hw1f_vega_result* out);
+/* the whole q3 sequence with the reference's draw windows: pathwise on normals [0,n),
+ * FD-/+ on [n,2n), recalibrated curves on [2n,2n+N_STEPS) and prices on [2n,3n) */
+int hw1f_vega(hw1f_engine* eng, hw1f_rng* rng, float S1, float S2, float K,
+              const float* P_mkt, const float* f_mkt, float eps, int32_t n_steps_S1,
+              hw1f_vega_result* out);
+/* the 20-run validation of src/3:527-568 as one launch with a seed axis; vega[n_runs] */
+int hw1f_vega_pathwise_batch(hw1f_engine* eng, const uint64_t* seeds, int32_t n_runs, uint64_t n_paths,
+                             float S1, float S2, float K, const float* P_mkt, const float* f_mkt,
+                             int32_t n_steps_S1, float* vega, float* sim_ms);
+
+/* ---- fused pass (BASELINE.json scaling run) --------------------------------------------- */
+/* One launch: antithetic curve sums on the maturity grid + ZBC/control moments + pathwise-vega
+ * tangent (both antithetic twins) evaluated at step n_steps_S1, all on the same normals.
+ * d_moments layout: [0,2*n_mat) curve {sum,sumsq}; then 5 ZBC moments; then {sum v, sum v^2}. */
+#define HW1F_FUSED_EXTRA 7
+int hw1f_fused_moments(hw1f_engine* eng, hw1f_rng* rng, float S1, float S2, float K,
+                       const float* P_mkt, const float* f_mkt, int32_t n_steps_S1, double* d_moments);
+
+/* ---- sample trajectories -------------------------------------------------------------- */
+/* simulate_paths_show<<<1,32>>> (market_data.cuh:136-160; src/1:163): r_paths[n_show*(n_steps+1)].
+ * Does NOT advance rng (the reference's write-back is commented out, market_data.cuh:159). */
+int hw1f_sample_paths(hw1f_engine* eng, const hw1f_rng* rng, int32_t n_show, float* r_paths);
+
+/* ---- reduction benchmark ---------------------------------------------------------------- */
+/* benchmark_kernel() of src/benchmark_reductions.cu:17-72 for one method:
+ * 0 naive atomics, 1 shared-memory tree, 2 warp+block shuffle (perf_benchmark.cuh:19-197),
+ * 3 the engine's deterministic two-level tree.  Advances rng by n_steps_S1 per launch. */
+int hw1f_reduction_bench(hw1f_engine* eng, hw1f_rng* rng, int32_t method, float S1, float S2, float K,
+                         const float* P_mkt, const float* f_mkt, int32_t n_steps_S1,
+                         int32_t n_warmup, int32_t n_runs, float* avg_ms, float* price);
+
+/* ---- introspection used by the parity tests ------------------------------------------------ */
+/* raw XORWOW words derived ON THE GPU for path `path` of rng at its current offset:
+ * state[6] = {d, v0..v4} then n_draws outputs of curand() */
+int hw1f_debug_rng(hw1f_engine* eng, const hw1f_rng* rng, uint64_t path, int32_t n_draws,
+                   uint32_t* state6, uint32_t* draws);
+/* the first n normals of path `path` as the kernels generate them */
+int hw1f_debug_normals(hw1f_engine* eng, const hw1f_rng* rng, uint64_t path, int32_t n, float* out);
+/* HOST-side evaluation of the engine's jump algebra (no GPU): the XORWOW words after
+ * curand_init(seed, path, 2*floor(normal_offset/2)): state6 = {d, v0..v4} */
+int hw1f_host_rng_state(uint64_t seed, uint64_t path, uint64_t normal_offset, uint32_t* state6);
+/* pipe-throughput micro-kernels that give the roofline denominators on this GPU: which =
+ * 0 FFMA, 1 FFMA2, 2 MUFU.EX2, 3 SHF/LOP3, 4 I2FP.F32.U32, 5 MUFU+I2FP, 6 HW1F-like mix, 7 FMUL2.
+ * ms = event time of one launch, thread_instr = probed instructions executed (all threads). */
+int hw1f_pipe_probe(hw1f_engine* eng, int32_t which, int32_t iters, float* ms, double* thread_instr);
+/* number of kernel launches issued by this engine since creation */
+int hw1f_launch_count(const hw1f_engine* eng, uint64_t* n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HW1F_H */

@@ -1,0 +1,1189 @@
+// hw1f_api.cu -- implementation of the C ABI declared in include/hw1f.h.
+//
+// Host side of the engine: model constants (host float32 arithmetic in the reference's order,
+// common.cuh:60-110), per-device jump tables, launch orchestration on one CUDA stream, and the
+// float32 estimator algebra of the reference drivers.  No CPU fallback exists: if a CUDA call
+// fails the entry point returns an error code and hw1f_last_error() says why.
+#include "../../include/hw1f.h"
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "hw1f_kernels.cuh"
+#include "hw1f_probe.cuh"
+#include "xorwow_jump.hpp"
+
+using namespace hw1f;
+
+// ---------------------------------------------------------------------------------------------
+struct hw1f_rng {
+    uint64_t seed, first_path, n_paths, offset;   // offset counted in normals
+};
+
+namespace {
+
+template <class T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t cap = 0;   // elements
+    cudaError_t ensure(size_t n)
+    {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMalloc(&p, n * sizeof(T));
+        if (e == cudaSuccess) cap = n;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct Scenario {
+    float sigma, sig_st;
+    int drift_slot;    // which device drift table
+};
+
+}  // namespace
+
+struct hw1f_engine {
+    int device = -1;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr, own_stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_stage = nullptr;
+    std::string err = "";
+    uint64_t launches = 0;
+
+    bool has_model = false;
+    hw1f_params p{};
+    float dt = 0, spacing = 0, exp_adt = 0, sig_st = 0;
+    int stride = 0;
+    std::vector<float> h_drift, h_sdrift;
+
+    DevBuf<uint32_t> d_Jpow2;            // [kNumPow][800]
+    DevBuf<uint32_t> d_W;                // window tables
+    uint32_t W_hi_base = 0, W_n_hi = 0, W_L_log2 = 0;
+    DevBuf<uint32_t> d_U;                // [n_runs][5][L]
+    // drift tables, duplicated float2: slot 0 base, 1 sensitivity, 2/3 bumped scenarios
+    DevBuf<float2> d_drift[4];
+    DevBuf<float> d_mkt;                 // [4][n_mat]: P0,f0,P1,f1
+    DevBuf<BondPlan> d_plans;
+    DevBuf<double> d_partials;
+    DevBuf<double> d_moments;            // internal moment vector
+    DevBuf<float> d_out;                 // epilogue outputs
+    DevBuf<int> d_int;
+    void* h_stage = nullptr;             // pinned
+    size_t h_stage_bytes = 0;
+};
+
+namespace {
+
+#define HW_CUDA(eng, call)                                                                       \
+    do {                                                                                         \
+        cudaError_t _e = (call);                                                                 \
+        if (_e != cudaSuccess) {                                                                 \
+            (eng)->err = std::string(#call) + ": " + cudaGetErrorString(_e);                     \
+            return HW1F_ERR_CUDA;                                                                \
+        }                                                                                        \
+    } while (0)
+
+#define HW_REQUIRE(eng, cond, msg)                                                               \
+    do {                                                                                         \
+        if (!(cond)) { (eng)->err = (msg); return HW1F_ERR_INVALID; }                            \
+    } while (0)
+
+#define HW_TRY(expr)                                                                             \
+    do { int _s = (expr); if (_s != HW1F_OK) return _s; } while (0)
+
+int check_launch(hw1f_engine* e, const char* what)
+{
+    cudaError_t err = cudaGetLastError();
+    ++e->launches;
+    if (err != cudaSuccess) {
+        e->err = std::string(what) + ": " + cudaGetErrorString(err);
+        return HW1F_ERR_CUDA;
+    }
+    return HW1F_OK;
+}
+
+// ---- host model constants: the reference's host float32 expressions -------------------------
+void host_drift_tables(const hw1f_params& p, float sigma, float* drift, float* sdrift)
+{
+    // compute_drift_tables, common.cuh:60-84
+    const float H_A = p.a, H_DT = p.T_final / p.n_steps;
+    const float h_exp_adt = expf(-H_A * H_DT);
+    const float om_a = (1.0f - h_exp_adt) / H_A;
+    const float om_a_sq = om_a / H_A;
+    for (int i = 0; i < p.n_steps; ++i) {
+        const float s = i * H_DT;
+        const float t = (i + 1) * H_DT;
+        const float first_term = ((s + H_DT) - h_exp_adt * s) / H_A - om_a_sq;
+        if (drift)
+            drift[i] = (s < p.theta_break) ? (p.theta_b0 * first_term + p.theta_a0 * om_a)
+                                           : (p.theta_b1 * first_term + p.theta_a1 * om_a);
+        if (sdrift) {
+            const float sigma_term = (2.0f * sigma * expf(-H_A * t)) * (coshf(H_A * t) - coshf(H_A * s));
+            sdrift[i] = sigma_term / (H_A * H_A);
+        }
+    }
+}
+
+void host_shifted_drift_table(const hw1f_params& p, float sigma_new, float sigma_old, float* out)
+{
+    // compute_shifted_drift_table, src/3_sensitivity_analysis.cu:374-398
+    const float H_A = p.a, H_DT = p.T_final / p.n_steps;
+    const float shift_coeff = (sigma_new * sigma_new - sigma_old * sigma_old) / (2.0f * H_A);
+    const float h_exp_adt = expf(-H_A * H_DT);
+    const float om_a = (1.0f - h_exp_adt) / H_A;
+    const float om_a_sq = om_a / H_A;
+    for (int i = 0; i < p.n_steps; ++i) {
+        const float s = i * H_DT;
+        const float t = (i + 1) * H_DT;
+        const float first_term = ((s + H_DT) - h_exp_adt * s) / H_A - om_a_sq;
+        const float base = (s < p.theta_break) ? (p.theta_b0 * first_term + p.theta_a0 * om_a)
+                                               : (p.theta_b1 * first_term + p.fd_theta_a1 * om_a);
+        const float adj = (shift_coeff / H_A) *
+                          (1.0f + expf(-2.0f * H_A * t) - expf(-H_A * (t - s)) - expf(-H_A * (t + s)));
+        out[i] = base + adj;
+    }
+}
+
+float host_sig_st(const hw1f_params& p, float sigma)
+{
+    // compute_h_sig_st, common.cuh:87-89
+    const float H_DT = p.T_final / p.n_steps;
+    return sigma * sqrtf((1.0f - expf(-2.0f * p.a * H_DT)) / (2.0f * p.a));
+}
+
+// ---- staging ---------------------------------------------------------------------------------
+int stage_reserve(hw1f_engine* e, size_t bytes)
+{
+    if (bytes <= e->h_stage_bytes) return HW1F_OK;
+    if (e->h_stage) cudaFreeHost(e->h_stage);
+    e->h_stage = nullptr;
+    e->h_stage_bytes = 0;
+    HW_CUDA(e, cudaMallocHost(&e->h_stage, bytes));
+    e->h_stage_bytes = bytes;
+    return HW1F_OK;
+}
+
+// host -> device through the pinned buffer, stream ordered; waits for the previous upload only
+int upload(hw1f_engine* e, void* dst, const void* src, size_t bytes)
+{
+    HW_CUDA(e, cudaEventSynchronize(e->ev_stage));
+    HW_TRY(stage_reserve(e, bytes));
+    memcpy(e->h_stage, src, bytes);
+    HW_CUDA(e, cudaMemcpyAsync(dst, e->h_stage, bytes, cudaMemcpyHostToDevice, e->stream));
+    HW_CUDA(e, cudaEventRecord(e->ev_stage, e->stream));
+    return HW1F_OK;
+}
+
+// device -> host through the pinned buffer; synchronises the stream
+int download(hw1f_engine* e, void* dst, const void* src, size_t bytes)
+{
+    HW_CUDA(e, cudaEventSynchronize(e->ev_stage));
+    HW_TRY(stage_reserve(e, bytes));
+    HW_CUDA(e, cudaMemcpyAsync(e->h_stage, src, bytes, cudaMemcpyDeviceToHost, e->stream));
+    HW_CUDA(e, cudaStreamSynchronize(e->stream));
+    memcpy(dst, e->h_stage, bytes);
+    return HW1F_OK;
+}
+
+int upload_drift(hw1f_engine* e, int slot, const float* table)
+{
+    const int n = e->p.n_steps;
+    HW_CUDA(e, e->d_drift[slot].ensure(n + 2));
+    std::vector<float2> dup(n + 2);
+    for (int i = 0; i < n; ++i) dup[i] = make_float2(table[i], table[i]);
+    dup[n] = dup[n + 1] = make_float2(0.f, 0.f);
+    return upload(e, e->d_drift[slot].p, dup.data(), dup.size() * sizeof(float2));
+}
+
+ModelDev model_dev(const hw1f_engine* e)
+{
+    ModelDev m;
+    m.r0 = e->p.r0;
+    m.exp_adt = e->exp_adt;
+    m.dt = e->dt;
+    m.a = e->p.a;
+    m.spacing = e->spacing;
+    m.inv_spacing = 1.0f / e->spacing;   // the compiler folds x/0.1f to x*10.0f in the reference
+    m.neg_spacing = -e->spacing;
+    m.n_steps = e->p.n_steps;
+    m.n_mat = e->p.n_mat;
+    m.stride = e->stride;
+    return m;
+}
+
+// ---- stream geometry: window tables for the hi part, U table for the lo part -------------------
+struct Launch {
+    StreamGeom g;
+    SeedArgs seeds;
+    int n_runs;
+    unsigned grid_x;
+    int lead;          // 1 if the launch starts on the cos half of a Box-Muller pair
+};
+
+uint32_t pick_L_log2(uint64_t n_paths)
+{
+    uint32_t lg = 0;
+    while ((1ull << lg) < n_paths) ++lg;
+    uint32_t L = lg / 2 + 1;
+    if (L < (uint32_t)kChunkLog2) L = kChunkLog2;
+    if (L > 16) L = 16;
+    return L;
+}
+
+int ensure_tables(hw1f_engine* e)
+{
+    if (e->d_Jpow2.p) return HW1F_OK;
+    const std::vector<uint32_t> flat = jump_tables().flat_seq();
+    HW_CUDA(e, e->d_Jpow2.ensure(flat.size()));
+    HW_CUDA(e, cudaMemcpyAsync(e->d_Jpow2.p, flat.data(), flat.size() * sizeof(uint32_t), cudaMemcpyHostToDevice,
+                               e->stream));
+    HW_CUDA(e, cudaStreamSynchronize(e->stream));
+    return HW1F_OK;
+}
+
+int ensure_windows(hw1f_engine* e, uint32_t L_log2, uint32_t hi_first, uint32_t hi_last)
+{
+    if (e->d_W.p && e->W_L_log2 == L_log2 && hi_first >= e->W_hi_base && hi_last < e->W_hi_base + e->W_n_hi)
+        return HW1F_OK;
+    const uint32_t n_hi = hi_last - hi_first + 1;
+    HW_CUDA(e, e->d_W.ensure((size_t)n_hi * kWinWords));
+    build_hi_kernel<<<n_hi, 160, 0, e->stream>>>(hi_first, L_log2, e->d_Jpow2.p, e->d_W.p);
+    HW_TRY(check_launch(e, "build_hi_kernel"));
+    e->W_L_log2 = L_log2;
+    e->W_hi_base = hi_first;
+    e->W_n_hi = n_hi;
+    return HW1F_OK;
+}
+
+// Prepare a launch over `n_runs` seeds sharing (first_path, n_paths, normal offset).
+int prepare_launch(hw1f_engine* e, const uint64_t* seeds, int n_runs, uint64_t first_path, uint64_t n_paths,
+                   uint64_t normal_offset, Launch* L)
+{
+    HW_REQUIRE(e, n_runs >= 1 && n_runs <= kMaxRuns, "n_runs must be in [1,32]");
+    HW_REQUIRE(e, n_paths >= 1, "n_paths must be >= 1");
+    HW_REQUIRE(e, first_path + n_paths >= first_path, "path range overflows 64 bits");
+    HW_TRY(ensure_tables(e));
+    const uint32_t L_log2 = pick_L_log2(n_paths);
+    const uint64_t last_path = first_path + n_paths - 1;
+    const uint64_t hi_first = first_path >> L_log2, hi_last = last_path >> L_log2;
+    HW_REQUIRE(e, hi_last < (1ull << 32), "path index too large for the jump tables (>= 2^41)");
+    HW_TRY(ensure_windows(e, L_log2, (uint32_t)hi_first, (uint32_t)hi_last));
+    const uint32_t Lsz = 1u << L_log2;
+    HW_CUDA(e, e->d_U.ensure((size_t)n_runs * 5 * Lsz));
+
+    // seed scramble + offset jump on the host (one 160-bit vector per run)
+    const uint64_t draw_offset = 2 * (normal_offset / 2);
+    const JumpTables& jt = jump_tables();
+    for (int r = 0; r < n_runs; ++r) {
+        BitVec v;
+        const uint32_t d0 = seed_scramble(seeds[r], v);
+        uint64_t off = draw_offset;
+        for (int k = 0; off != 0 && k < kNumPow; ++k, off >>= 1)
+            if (off & 1) v = jt.step_pow2[k].apply(v);
+        HW_REQUIRE(e, off == 0, "normal offset too large (>= 2^48)");
+        for (int w = 0; w < 5; ++w) L->seeds.s[r].v0[w] = v[w];
+        L->seeds.s[r].d_start = d0 + kWeyl * (uint32_t)draw_offset;
+    }
+    for (int r = n_runs; r < kMaxRuns; ++r) L->seeds.s[r] = L->seeds.s[0];
+    L->n_runs = n_runs;
+    L->lead = (int)(normal_offset & 1);
+
+    const unsigned long long total_warps = (unsigned long long)n_runs * Lsz;
+    const unsigned prep_blocks = (unsigned)((total_warps + 7) / 8);
+    prep_lo_kernel<<<prep_blocks, 256, 0, e->stream>>>(L->seeds, n_runs, L_log2, e->d_Jpow2.p, e->d_U.p);
+    HW_TRY(check_launch(e, "prep_lo_kernel"));
+
+    StreamGeom& g = L->g;
+    g.W = e->d_W.p;
+    g.U = e->d_U.p;
+    g.first_path = first_path;
+    g.n_paths = n_paths;
+    g.chunk0 = first_path >> kChunkLog2;
+    g.n_chunks = (last_path >> kChunkLog2) - g.chunk0 + 1;
+    g.hi_base = e->W_hi_base;
+    g.L_log2 = L_log2;
+    // one wave of resident blocks per grid-stride pass keeps the partials small at 2^30 paths
+    const unsigned long long cap = (unsigned long long)e->sm_count * 32ull;
+    L->grid_x = (unsigned)(g.n_chunks < cap ? g.n_chunks : cap);
+    return HW1F_OK;
+}
+
+int reduce_to(hw1f_engine* e, int n_runs, unsigned n_blocks, int nq, double* d_out)
+{
+    reduce_partials_kernel<double><<<dim3(nq, n_runs), 256, 0, e->stream>>>(e->d_partials.p, (int)n_blocks, nq, d_out);
+    return check_launch(e, "reduce_partials_kernel");
+}
+
+int require_model(hw1f_engine* e)
+{
+    if (!e) return HW1F_ERR_INVALID;
+    if (!e->has_model) { e->err = "hw1f_set_model() has not been called"; return HW1F_ERR_NO_MODEL; }
+    return HW1F_OK;
+}
+
+int resolve_steps(hw1f_engine* e, float S1, int32_t n_in, int32_t* n_out)
+{
+    if (n_in >= 0) { *n_out = n_in; }
+    else HW_TRY(hw1f_steps_to(e, S1, n_out));
+    HW_REQUIRE(e, *n_out >= 0 && *n_out <= e->p.n_steps, "n_steps_S1 outside [0, n_steps]");
+    return HW1F_OK;
+}
+
+// bond plans for up to two scenarios; market set s at d_mkt[2s], d_mkt[2s+1]
+int launch_plans(hw1f_engine* e, const ScenDev* sc, int n_scen, float S1, float S2)
+{
+    const int n = e->p.n_mat;
+    HW_CUDA(e, e->d_plans.ensure(kMaxScen));
+    const float* P0 = e->d_mkt.p;
+    const float* f0 = P0 + n;
+    const float* P1 = P0 + 2 * n;
+    const float* f1 = P0 + 3 * n;
+    bond_plan_kernel<<<1, 32, 0, e->stream>>>(model_dev(e), sc[0], sc[n_scen > 1 ? 1 : 0], n_scen, S1, S2, P0, f0,
+                                              n_scen > 1 ? P1 : P0, n_scen > 1 ? f1 : f0, e->d_plans.p);
+    return check_launch(e, "bond_plan_kernel");
+}
+
+int upload_market(hw1f_engine* e, int set, const float* P_mkt, const float* f_mkt)
+{
+    const int n = e->p.n_mat;
+    HW_CUDA(e, e->d_mkt.ensure(4 * (size_t)n));
+    std::vector<float> tmp(2 * (size_t)n);
+    memcpy(tmp.data(), P_mkt, n * sizeof(float));
+    memcpy(tmp.data() + n, f_mkt, n * sizeof(float));
+    return upload(e, e->d_mkt.p + 2 * (size_t)set * n, tmp.data(), tmp.size() * sizeof(float));
+}
+
+ScenDev scen_dev(const hw1f_engine* e, float sigma, float sig_st, int drift_slot)
+{
+    ScenDev s;
+    s.sigma = sigma;
+    s.sig_st = sig_st;
+    s.drift2 = e->d_drift[drift_slot].p;
+    s.sdrift2 = e->d_drift[1].p;
+    return s;
+}
+
+size_t smem_curve(const hw1f_engine* e, int nscen, bool with_sq)
+{
+    const int nq = nscen * (with_sq ? 2 : 1) * e->p.n_mat;
+    return (size_t)kWinWords * 4 + (size_t)nscen * (e->p.n_steps / 2) * sizeof(float4) + (size_t)kWarps * nq * sizeof(double);
+}
+
+template <class K>
+int set_smem(hw1f_engine* e, K kernel, size_t bytes)
+{
+    HW_CUDA(e, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    HW_CUDA(e, cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                    (int)cudaSharedmemCarveoutMaxShared));
+    return HW1F_OK;
+}
+
+// ---- Q1 launch: sums for NSCEN scenarios into d_moments[n_runs][nscen*2*n_mat] -----------------
+int launch_curve(hw1f_engine* e, const Launch& L, const ScenDev* sc, int nscen, double* d_moments)
+{
+    const int nq = nscen * 2 * e->p.n_mat;
+    HW_CUDA(e, e->d_partials.ensure((size_t)L.n_runs * L.grid_x * nq));
+    const size_t smem = smem_curve(e, nscen, true);
+    const dim3 grid(L.grid_x, L.n_runs);
+    if (nscen == 1) {
+        HW_TRY(set_smem(e, bond_curve_kernel<true, 1>, smem));
+        bond_curve_kernel<true, 1><<<grid, kThreads, smem, e->stream>>>(L.g, L.seeds, model_dev(e), sc[0], sc[0],
+                                                                        e->d_partials.p);
+    } else {
+        HW_TRY(set_smem(e, bond_curve_kernel<true, 2>, smem));
+        bond_curve_kernel<true, 2><<<grid, kThreads, smem, e->stream>>>(L.g, L.seeds, model_dev(e), sc[0], sc[1],
+                                                                        e->d_partials.p);
+    }
+    HW_TRY(check_launch(e, "bond_curve_kernel"));
+    return reduce_to(e, L.n_runs, L.grid_x, nq, d_moments);
+}
+
+int launch_zbc(hw1f_engine* e, const Launch& L, const ScenDev* sc, int nscen, int n_steps_S1, float K,
+               double* d_moments)
+{
+    const int nq = nscen * 5;
+    HW_CUDA(e, e->d_partials.ensure((size_t)L.n_runs * L.grid_x * nq));
+    const size_t smem = (size_t)kWinWords * 4 + (size_t)nscen * ((n_steps_S1 + 1) / 2 + 1) * sizeof(float4);
+    const dim3 grid(L.grid_x, L.n_runs);
+    if (nscen == 1) {
+        HW_TRY(set_smem(e, zbc_kernel<1>, smem));
+        zbc_kernel<1><<<grid, kThreads, smem, e->stream>>>(L.g, L.seeds, model_dev(e), sc[0], sc[0], e->d_plans.p,
+                                                           n_steps_S1, L.lead, K, e->d_partials.p);
+    } else {
+        HW_TRY(set_smem(e, zbc_kernel<2>, smem));
+        zbc_kernel<2><<<grid, kThreads, smem, e->stream>>>(L.g, L.seeds, model_dev(e), sc[0], sc[1], e->d_plans.p,
+                                                           n_steps_S1, L.lead, K, e->d_partials.p);
+    }
+    HW_TRY(check_launch(e, "zbc_kernel"));
+    return reduce_to(e, L.n_runs, L.grid_x, nq, d_moments);
+}
+
+int launch_pathwise(hw1f_engine* e, const Launch& L, const ScenDev& sc, int n_steps_S1, float K, double* d_moments)
+{
+    HW_CUDA(e, e->d_partials.ensure((size_t)L.n_runs * L.grid_x * 2));
+    const size_t smem = (size_t)kWinWords * 4 + (size_t)(n_steps_S1 + 1) * sizeof(float4);
+    HW_TRY(set_smem(e, pathwise_kernel, smem));
+    pathwise_kernel<<<dim3(L.grid_x, L.n_runs), kThreads, smem, e->stream>>>(L.g, L.seeds, model_dev(e), sc,
+                                                                            e->d_plans.p, n_steps_S1, L.lead, K,
+                                                                            e->d_partials.p);
+    HW_TRY(check_launch(e, "pathwise_kernel"));
+    return reduce_to(e, L.n_runs, L.grid_x, 2, d_moments);
+}
+
+// float32 host algebra of src/2:154-179 / :259-290 (+ double extras)
+void zbc_algebra(const double mom[5], uint64_t n_paths_total, float P0S2, int32_t n_steps_S1, hw1f_zbc_result* r)
+{
+    memset(r, 0, sizeof(*r));
+    for (int k = 0; k < 5; ++k) r->mom[k] = mom[k];
+    const int N_total = (int)(2 * n_paths_total);
+    r->n_total = 2 * n_paths_total;
+    r->n_steps_S1 = n_steps_S1;
+    const float h_ZBC = (float)mom[0], h_control = (float)mom[1], h_ZBC_sq = (float)mom[2],
+                h_control_sq = (float)mom[3], h_cross = (float)mom[4];
+    const float mean_ZBC = h_ZBC / N_total;
+    const float mean_control = h_control / N_total;
+    const float E_Y2 = h_control_sq / N_total;
+    const float E_Y_sq = mean_control * mean_control;
+    const float var_control = E_Y2 - E_Y_sq;
+    const float E_XY = h_cross / N_total;
+    const float E_X_E_Y = mean_ZBC * mean_control;
+    const float cov = E_XY - E_X_E_Y;
+    const float beta = cov / var_control;
+    const float control_adjustment = beta * (mean_control - P0S2);
+    const float adjusted = mean_ZBC - control_adjustment;
+    const float corr_single = cov / (sqrtf(var_control) * sqrtf(E_Y2 - E_Y_sq));
+    const float E_X2 = h_ZBC_sq / N_total;
+    const float var_ZBC = E_X2 - mean_ZBC * mean_ZBC;
+    const float corr = cov / sqrtf(var_ZBC * var_control);
+    r->mean_X = mean_ZBC; r->mean_Y = mean_control; r->var_X = var_ZBC; r->var_Y = var_control;
+    r->cov = cov; r->beta = beta; r->control_adjustment = control_adjustment;
+    r->price_raw = mean_ZBC; r->price_cv = adjusted; r->corr_single = corr_single; r->corr = corr;
+    // double-precision companions.  The per-thread samples are antithetic pair sums, so the
+    // i.i.d. unit is the pair: x = X/2, y = Y/2 with n = n_paths_total samples.
+    const double n = (double)n_paths_total;
+    const double mx = mom[0] / (2.0 * n), my = mom[1] / (2.0 * n);
+    const double vyy = mom[3] / (2.0 * n) - my * my, cxy = mom[4] / (2.0 * n) - mx * my;
+    const double b = (vyy > 0) ? cxy / vyy : 0.0;
+    r->beta_f64 = b;
+    r->price_cv_f64 = mx - b * (my - (double)P0S2);
+    // standard errors: per-path second moments are an upper bound for the pair-mean variance
+    const double vxx = mom[2] / (2.0 * n) - mx * mx;
+    const double var_cv = vxx - 2.0 * b * cxy + b * b * vyy;
+    r->se_raw = (vxx > 0) ? sqrt(vxx / (2.0 * n)) : 0.0;
+    r->se_cv = (var_cv > 0) ? sqrt(var_cv / (2.0 * n)) : 0.0;
+    r->ci95_lo = r->price_cv_f64 - 1.959963984540054 * r->se_cv;
+    r->ci95_hi = r->price_cv_f64 + 1.959963984540054 * r->se_cv;
+}
+
+}  // namespace
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+extern "C" {
+
+int hw1f_abi_version(void) { return HW1F_ABI_VERSION; }
+
+const char* hw1f_status_string(int s)
+{
+    switch (s) {
+        case HW1F_OK: return "ok";
+        case HW1F_ERR_INVALID: return "invalid argument";
+        case HW1F_ERR_CUDA: return "CUDA error";
+        case HW1F_ERR_NO_DEVICE: return "no CUDA device";
+        case HW1F_ERR_UNSUPPORTED: return "unsupported configuration";
+        case HW1F_ERR_NO_MODEL: return "model not set";
+        default: return "unknown status";
+    }
+}
+
+const char* hw1f_last_error(const hw1f_engine* e) { return e ? e->err.c_str() : "null engine"; }
+
+int hw1f_engine_create(int device, hw1f_engine** out)
+{
+    if (!out) return HW1F_ERR_INVALID;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) { cudaGetLastError(); return HW1F_ERR_NO_DEVICE; }
+    if (device < 0) {   // select_gpu(), common.cuh:122-141
+        size_t best_free = 0;
+        device = 0;
+        for (int i = 0; i < count; ++i) {
+            size_t fr = 0, tot = 0;
+            if (cudaSetDevice(i) == cudaSuccess && cudaMemGetInfo(&fr, &tot) == cudaSuccess && fr > best_free) {
+                best_free = fr;
+                device = i;
+            }
+        }
+    }
+    if (device >= count) return HW1F_ERR_NO_DEVICE;
+    hw1f_engine* e = new (std::nothrow) hw1f_engine();
+    if (!e) return HW1F_ERR_INVALID;
+    e->device = device;
+    cudaDeviceProp prop;
+    if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
+        delete e;
+        return HW1F_ERR_CUDA;
+    }
+    if (prop.major < 10) {   // sm_100a binary only: fail loudly instead of a confusing launch error
+        delete e;
+        return HW1F_ERR_UNSUPPORTED;
+    }
+    e->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&e->ev0) != cudaSuccess || cudaEventCreate(&e->ev1) != cudaSuccess ||
+        cudaEventCreateWithFlags(&e->ev_stage, cudaEventDisableTiming) != cudaSuccess) {
+        delete e;
+        return HW1F_ERR_CUDA;
+    }
+    e->stream = e->own_stream;
+    *out = e;
+    return HW1F_OK;
+}
+
+int hw1f_engine_destroy(hw1f_engine* e)
+{
+    if (!e) return HW1F_OK;
+    cudaSetDevice(e->device);
+    cudaStreamSynchronize(e->stream);
+    e->d_Jpow2.release(); e->d_W.release(); e->d_U.release();
+    for (auto& d : e->d_drift) d.release();
+    e->d_mkt.release(); e->d_plans.release(); e->d_partials.release(); e->d_moments.release();
+    e->d_out.release(); e->d_int.release();
+    if (e->h_stage) cudaFreeHost(e->h_stage);
+    if (e->ev0) cudaEventDestroy(e->ev0);
+    if (e->ev1) cudaEventDestroy(e->ev1);
+    if (e->ev_stage) cudaEventDestroy(e->ev_stage);
+    if (e->own_stream) cudaStreamDestroy(e->own_stream);
+    delete e;
+    return HW1F_OK;
+}
+
+int hw1f_engine_set_stream(hw1f_engine* e, void* s)
+{
+    if (!e) return HW1F_ERR_INVALID;
+    HW_CUDA(e, cudaSetDevice(e->device));
+    HW_CUDA(e, cudaStreamSynchronize(e->stream));
+    e->stream = s ? (cudaStream_t)s : e->own_stream;
+    return HW1F_OK;
+}
+
+int hw1f_engine_device(const hw1f_engine* e, int* d)
+{
+    if (!e || !d) return HW1F_ERR_INVALID;
+    *d = e->device;
+    return HW1F_OK;
+}
+
+int hw1f_engine_synchronize(hw1f_engine* e)
+{
+    if (!e) return HW1F_ERR_INVALID;
+    HW_CUDA(e, cudaSetDevice(e->device));
+    HW_CUDA(e, cudaStreamSynchronize(e->stream));
+    return HW1F_OK;
+}
+
+int hw1f_default_params(hw1f_params* p)
+{
+    if (!p) return HW1F_ERR_INVALID;
+    p->a = 1.0f; p->sigma = 0.1f; p->r0 = 0.012f;            // common.cuh:37-39
+    p->T_final = 10.0f; p->n_steps = 1000; p->n_mat = 101;   // common.cuh:16-22
+    p->theta_a0 = 0.012f; p->theta_b0 = 0.0014f;             // common.cuh:229
+    p->theta_a1 = 0.019f; p->theta_b1 = 0.001f;
+    p->theta_break = 5.0f;
+    p->fd_theta_a1 = 0.014f;                                 // src/3:387
+    return HW1F_OK;
+}
+
+int hw1f_set_model(hw1f_engine* e, const hw1f_params* p)
+{
+    if (!e || !p) return HW1F_ERR_INVALID;
+    HW_REQUIRE(e, p->n_mat >= 3 && p->n_mat <= 1024, "n_mat must be in [3,1024]");
+    HW_REQUIRE(e, p->n_steps >= 2 && p->n_steps <= 8192, "n_steps must be in [2,8192]");
+    HW_REQUIRE(e, p->n_steps % (p->n_mat - 1) == 0, "N_STEPS must be evenly divisible by (N_MAT - 1)");  // common.cuh:25-27
+    HW_REQUIRE(e, p->a > 0.0f && p->sigma > 0.0f && p->T_final > 0.0f, "a, sigma, T_final must be positive");
+    HW_CUDA(e, cudaSetDevice(e->device));
+    e->p = *p;
+    e->dt = p->T_final / p->n_steps;                  // H_DT, common.cuh:33
+    e->spacing = p->T_final / (p->n_mat - 1);         // H_MAT_SPACING, common.cuh:34
+    e->exp_adt = expf(-p->a * e->dt);                 // common.cuh:93
+    e->sig_st = host_sig_st(*p, p->sigma);            // common.cuh:94
+    e->stride = p->n_steps / (p->n_mat - 1);          // SAVE_STRIDE, common.cuh:29
+    e->h_drift.assign(p->n_steps, 0.f);
+    e->h_sdrift.assign(p->n_steps, 0.f);
+    host_drift_tables(*p, p->sigma, e->h_drift.data(), e->h_sdrift.data());
+    e->has_model = true;
+    HW_TRY(upload_drift(e, 0, e->h_drift.data()));
+    HW_TRY(upload_drift(e, 1, e->h_sdrift.data()));
+    return HW1F_OK;
+}
+
+int hw1f_get_model(const hw1f_engine* e, hw1f_params* out)
+{
+    if (!e || !out || !e->has_model) return HW1F_ERR_INVALID;
+    *out = e->p;
+    return HW1F_OK;
+}
+
+int hw1f_get_constants(const hw1f_engine* e, hw1f_constants* c)
+{
+    if (!e || !c || !e->has_model) return HW1F_ERR_INVALID;
+    c->dt = e->dt; c->mat_spacing = e->spacing; c->exp_adt = e->exp_adt; c->sig_st = e->sig_st;
+    c->save_stride = e->stride;
+    return HW1F_OK;
+}
+
+int hw1f_get_drift_table(const hw1f_engine* e, int which, float sigma, float* out)
+{
+    if (!e || !out || !e->has_model) return HW1F_ERR_INVALID;
+    if (which == 0) host_drift_tables(e->p, sigma, out, nullptr);
+    else if (which == 1) host_drift_tables(e->p, sigma, nullptr, out);
+    else if (which == 2) host_shifted_drift_table(e->p, sigma, e->p.sigma, out);
+    else return HW1F_ERR_INVALID;
+    return HW1F_OK;
+}
+
+int hw1f_steps_to(hw1f_engine* e, float S1, int32_t* n)
+{
+    HW_TRY(require_model(e));
+    if (!n) return HW1F_ERR_INVALID;
+    HW_CUDA(e, cudaSetDevice(e->device));
+    HW_CUDA(e, e->d_int.ensure(4));
+    steps_probe_kernel<<<1, 1, 0, e->stream>>>(S1, e->dt, e->d_int.p);
+    HW_TRY(check_launch(e, "steps_probe_kernel"));
+    int v = 0;
+    HW_TRY(download(e, &v, e->d_int.p, sizeof(int)));
+    *n = v;
+    return HW1F_OK;
+}
+
+// ---- RNG handle ------------------------------------------------------------------------------
+int hw1f_rng_create(uint64_t seed, uint64_t first_path, uint64_t n_paths, hw1f_rng** out)
+{
+    if (!out || n_paths == 0) return HW1F_ERR_INVALID;
+    hw1f_rng* r = new (std::nothrow) hw1f_rng{seed, first_path, n_paths, 0};
+    if (!r) return HW1F_ERR_INVALID;
+    *out = r;
+    return HW1F_OK;
+}
+int hw1f_rng_clone(const hw1f_rng* src, hw1f_rng** out)
+{
+    if (!src || !out) return HW1F_ERR_INVALID;
+    *out = new (std::nothrow) hw1f_rng(*src);
+    return *out ? HW1F_OK : HW1F_ERR_INVALID;
+}
+int hw1f_rng_destroy(hw1f_rng* r) { delete r; return HW1F_OK; }
+int hw1f_rng_tell(const hw1f_rng* r, uint64_t* off)
+{
+    if (!r || !off) return HW1F_ERR_INVALID;
+    *off = r->offset;
+    return HW1F_OK;
+}
+int hw1f_rng_seek(hw1f_rng* r, uint64_t off)
+{
+    if (!r) return HW1F_ERR_INVALID;
+    r->offset = off;
+    return HW1F_OK;
+}
+int hw1f_rng_info(const hw1f_rng* r, uint64_t* seed, uint64_t* first, uint64_t* n)
+{
+    if (!r) return HW1F_ERR_INVALID;
+    if (seed) *seed = r->seed;
+    if (first) *first = r->first_path;
+    if (n) *n = r->n_paths;
+    return HW1F_OK;
+}
+
+// ---- Q1 ----------------------------------------------------------------------------------------
+int hw1f_bond_curve_moments(hw1f_engine* e, hw1f_rng* rng, double* d_moments)
+{
+    HW_TRY(require_model(e));
+    if (!rng || !d_moments) return HW1F_ERR_INVALID;
+    HW_CUDA(e, cudaSetDevice(e->device));
+    if ((rng->offset & 1) || (e->stride & 1)) {
+        e->err = "bond curve needs an even normal offset and an even save stride";
+        return HW1F_ERR_UNSUPPORTED;
+    }
+    Launch L;
+    HW_TRY(prepare_launch(e, &rng->seed, 1, rng->first_path, rng->n_paths, rng->offset, &L));
+    const ScenDev sc = scen_dev(e, e->p.sigma, e->sig_st, 0);
+    HW_TRY(launch_curve(e, L, &sc, 1, d_moments));
+    rng->offset += (uint64_t)e->p.n_steps;
+    return HW1F_OK;
+}
+
+int hw1f_bond_curve_finish(hw1f_engine* e, const double* d_moments, uint64_t n_paths_total, float* P, float* f,
+                           float* P_se)
+{
+    HW_TRY(require_model(e));
+    if (!d_moments || !P || !f) return HW1F_ERR_INVALID;
+    HW_REQUIRE(e, 2 * n_paths_total < (1ull << 31), "the reference's (float)n_paths epilogue needs 2*n_paths < 2^31");
+    HW_CUDA(e, cudaSetDevice(e->device));
+    const int n = e->p.n_mat;
+    HW_CUDA(e, e->d_out.ensure(4 * (size_t)n));
+    float* dP = e->d_out.p;
+    float* df = dP + n;
+    float* dse = dP + 2 * n;
+    const float inv_dT = 1.0f / e->spacing;   // host division, src/1:76
+    curve_epilogue_kernel<<<1, ((n + 31) / 32) * 32, n * sizeof(float), e->stream>>>(d_moments, n, n_paths_total,
+                                                                                    inv_dT, dP, df, dse);
+    HW_TRY(check_launch(e, "curve_epilogue_kernel"));
+    std::vector<float> host(3 * (size_t)n);
+    HW_TRY(download(e, host.data(), dP, host.size() * sizeof(float)));
+    memcpy(P, host.data(), n * sizeof(float));
+    memcpy(f, host.data() + n, n * sizeof(float));
+    if (P_se) memcpy(P_se, host.data() + 2 * n, n * sizeof(float));
+    return HW1F_OK;
+}
+
+int hw1f_bond_curve(hw1f_engine* e, hw1f_rng* rng, float* P, float* f, float* P_se, float* sim_ms)
+{
+    HW_TRY(require_model(e));
+    if (!rng) return HW1F_ERR_INVALID;
+    HW_CUDA(e, cudaSetDevice(e->device));
+    HW_CUDA(e, e->d_moments.ensure(4 * (size_t)e->p.n_mat * kMaxRuns));
+    HW_CUDA(e, cudaEventRecord(e->ev0, e->stream));
+    HW_TRY(hw1f_bond_curve_moments(e, rng, e->d_moments.p));
+    HW_CUDA(e, cudaEventRecord(e->ev1, e->stream));
+    HW_TRY(hw1f_bond_curve_finish(e, e->d_moments.p, rng->n_paths, P, f, P_se));
+    if (sim_ms) HW_CUDA(e, cudaEventElapsedTime(sim_ms, e->ev0, e->ev1));
+    return HW1F_OK;
+}
+
+// ---- Q2a ----------------------------------------------------------------------------------------
+int hw1f_theta_calibrate(hw1f_engine* e, const float* f, float* theta_rec, float* theta_ref, float* T)
+{
+    HW_TRY(require_model(e));
+    if (!f || !theta_rec || !theta_ref || !T) return HW1F_ERR_INVALID;
+    HW_CUDA(e, cudaSetDevice(e->device));
+    const int n = e->p.n_mat;
+    HW_CUDA(e, e->d_out.ensure(4 * (size_t)n));
+    float* d_f = e->d_out.p;
+    HW_TRY(upload(e, d_f, f, n * sizeof(float)));
+    theta_kernel<<<1, n, 0, e->stream>>>(d_f, n, e->p.a, e->p.sigma, e->spacing, e->p.theta_a0, e->p.theta_b0,
+                                         e->p.theta_a1, e->p.theta_b1, e->p.theta_break, d_f + n, d_f + 2 * n,
+                                         d_f + 3 * n);
+    HW_TRY(check_launch(e, "theta_kernel"));
+    std::vector<float> host(3 * (size_t)n);
+    HW_TRY(download(e, host.data(), d_f + n, host.size() * sizeof(float)));
+    memcpy(theta_rec, host.data(), n * sizeof(float));
+    memcpy(theta_ref, host.data() + n, n * sizeof(float));
+    memcpy(T, host.data() + 2 * n, n * sizeof(float));
+    return HW1F_OK;
+}
+
+// ---- Q2b ----------------------------------------------------------------------------------------
+int hw1f_zbc_cv_moments(hw1f_engine* e, hw1f_rng* rng, float S1, float S2, float K, const float* P_mkt,
+                        const float* f_mkt, int32_t n_steps_S1, double* d_moments)
+{
+    HW_TRY(require_model(e));
+    if (!rng || !P_mkt || !f_mkt || !d_moments) return HW1F_ERR_INVALID;
+    HW_CUDA(e, cudaSetDevice(e->device));
+    int32_t n = 0;
+    HW_TRY(resolve_steps(e, S1, n_steps_S1, &n));
+    HW_TRY(upload_market(e, 0, P_mkt, f_mkt));
+    const ScenDev sc = scen_dev(e, e->p.sigma, e->sig_st, 0);
+    HW_TRY(launch_plans(e, &sc, 1, S1, S2));
+    Launch L;
+    HW_TRY(prepare_launch(e, &rng->seed, 1, rng->first_path, rng->n_paths, rng->offset, &L));
+    HW_TRY(launch_zbc(e, L, &sc, 1, n, K, d_moments));
+    rng->offset += (uint64_t)n;
+    return HW1F_OK;
+}
+
+int hw1f_zbc_cv_finish(hw1f_engine* e, const double* d_moments, uint64_t n_paths_total, float P0S2,
+                       hw1f_zbc_result* out)
+{
+    HW_TRY(require_model(e));
+    if (!d_moments || !out) return HW1F_ERR_INVALID;
+    HW_REQUIRE(e, 2 * n_paths_total < (1ull << 31), "the reference's int N_total needs 2*n_paths < 2^31");
+    HW_CUDA(e, cudaSetDevice(e->device));
+    double mom[5];
+    HW_TRY(download(e, mom, d_moments, sizeof(mom)));
+    zbc_algebra(mom, n_paths_total, P0S2, out->n_steps_S1, out);
+    return HW1F_OK;
+}
+
+int hw1f_zbc_cv(hw1f_engine* e, hw1f_rng* rng, float S1, float S2, float K, const float* P_mkt, const float* f_mkt,
+                int32_t n_steps_S1, hw1f_zbc_result* out, float* sim_ms)
+{
+    HW_TRY(require_model(e));
+    if (!rng || !out || !P_mkt) return HW1F_ERR_INVALID;
+    HW_CUDA(e, cudaSetDevice(e->device));
+    int32_t n = 0;
+    HW_TRY(resolve_steps(e, S1, n_steps_S1, &n));
+    HW_CUDA(e, e->d_moments.ensure(4 * (size_t)e->p.n_mat * kMaxRuns));
+    HW_CUDA(e, cudaEventRecord(e->ev0, e->stream));
+    HW_TRY(hw1f_zbc_cv_moments(e, rng, S1, S2, K, P_mkt, f_mkt, n, e->d_moments.p));
+    HW_CUDA(e, cudaEventRecord(e->ev1, e->stream));
+    out->n_steps_S1 = n;
+    HW_TRY(hw1f_zbc_cv_finish(e, e->d_moments.p, rng->n_paths, P_mkt[e->p.n_mat - 1], out));
+    out->n_steps_S1 = n;
+    if (sim_ms) HW_CUDA(e, cudaEventElapsedTime(sim_ms, e->ev0, e->ev1));
+    return HW1F_OK;
+}
+
+int hw1f_zbc_cv_batch(hw1f_engine* e, const uint64_t* seeds, int32_t n_runs, uint64_t n_paths, float S1, float S2,
+                      float K, const float* P_mkt, const float* f_mkt, int32_t n_steps_S1, hw1f_zbc_result* out,
+                      float* sim_ms)
+{
+    HW_TRY(require_model(e));
+    if (!seeds || !out || !P_mkt || !f_mkt) return HW1F_ERR_INVALID;
+    HW_REQUIRE(e, 2 * n_paths < (1ull << 31), "the reference's int N_total needs 2*n_paths < 2^31");
+    HW_CUDA(e, cudaSetDevice(e->device));
+    int32_t n = 0;
+    HW_TRY(resolve_steps(e, S1, n_steps_S1, &n));
+    HW_CUDA(e, e->d_moments.ensure(4 * (size_t)e->p.n_mat * kMaxRuns));
+    HW_TRY(upload_market(e, 0, P_mkt, f_mkt));
+    const ScenDev sc = scen_dev(e, e->p.sigma, e->sig_st, 0);
+    HW_TRY(launch_plans(e, &sc, 1, S1, S2));
+    HW_CUDA(e, cudaEventRecord(e->ev0, e->stream));
+    for (int32_t done = 0; done < n_runs; done += kMaxRuns) {
+        const int nb = (n_runs - done < kMaxRuns) ? (n_runs - done) : kMaxRuns;
+        Launch L;
+        HW_TRY(prepare_launch(e, seeds + done, nb, 0, n_paths, 0, &L));
+        HW_TRY(launch_zbc(e, L, &sc, 1, n, K, e->d_moments.p));
+        std::vector<double> mom(5 * (size_t)nb);
+        HW_TRY(download(e, mom.data(), e->d_moments.p, mom.size() * sizeof(double)));
+        for (int r = 0; r < nb; ++r) zbc_algebra(&mom[5 * r], n_paths, P_mkt[e->p.n_mat - 1], n, &out[done + r]);
+    }
+    HW_CUDA(e, cudaEventRecord(e->ev1, e->stream));
+    HW_CUDA(e, cudaEventSynchronize(e->ev1));
+    if (sim_ms) HW_CUDA(e, cudaEventElapsedTime(sim_ms, e->ev0, e->ev1));
+    return HW1F_OK;
+}
+
+// ---- Q3 ----------------------------------------------------------------------------------------
+int hw1f_vega_pathwise_moments(hw1f_engine* e, hw1f_rng* rng, float S1, float S2, float K, const float* P_mkt,
+                               const float* f_mkt, int32_t n_steps_S1, double* d_moments)
+{
+    HW_TRY(require_model(e));
+    if (!rng || !P_mkt || !f_mkt || !d_moments) return HW1F_ERR_INVALID;
+    HW_CUDA(e, cudaSetDevice(e->device));
+    int32_t n = 0;
+    HW_TRY(resolve_steps(e, S1, n_steps_S1, &n));
+    HW_TRY(upload_market(e, 0, P_mkt, f_mkt));
+    const ScenDev sc = scen_dev(e, e->p.sigma, e->sig_st, 0);
+    HW_TRY(launch_plans(e, &sc, 1, S1, S2));
+    Launch L;
+    HW_TRY(prepare_launch(e, &rng->seed, 1, rng->first_path, rng->n_paths, rng->offset, &L));
+    HW_TRY(launch_pathwise(e, L, sc, n, K, d_moments));
+    rng->offset += (uint64_t)n;
+    return HW1F_OK;
+}
+
+int hw1f_vega_pathwise(hw1f_engine* e, hw1f_rng* rng, float S1, float S2, float K, const float* P_mkt,
+                       const float* f_mkt, int32_t n_steps_S1, hw1f_vega_result* out)
+{
+    HW_TRY(require_model(e));
+    if (!rng || !out) return HW1F_ERR_INVALID;
+    HW_CUDA(e, cudaSetDevice(e->device));
+    int32_t n = 0;
+    HW_TRY(resolve_steps(e, S1, n_steps_S1, &n));
+    HW_CUDA(e, e->d_moments.ensure(4 * (size_t)e->p.n_mat * kMaxRuns));
+    HW_CUDA(e, cudaEventRecord(e->ev0, e->stream));
+    HW_TRY(hw1f_vega_pathwise_moments(e, rng, S1, S2, K, P_mkt, f_mkt, n, e->d_moments.p));
+    HW_CUDA(e, cudaEventRecord(e->ev1, e->stream));
+    double mom[2];
+    HW_TRY(download(e, mom, e->d_moments.p, sizeof(mom)));
+    const double np = (double)rng->n_paths;
+    out->n_steps_S1 = n;
+    out->vega_pathwise = (float)mom[0] / (float)(int)rng->n_paths;   // sum / N_PATHS in float, src/3:261
+    out->vega_pathwise_f64 = mom[0] / np;
+    const double var = (np > 1) ? (mom[1] - mom[0] * mom[0] / np) / (np - 1.0) : 0.0;
+    out->vega_pathwise_se = (var > 0) ? sqrt(var / np) : 0.0;
+    HW_CUDA(e, cudaEventElapsedTime(&out->ms_pathwise, e->ev0, e->ev1));
+    return HW1F_OK;
+}
+
+int hw1f_vega_pathwise_batch(hw1f_engine* e, const uint64_t* seeds, int32_t n_runs, uint64_t n_paths, float S1,
+                             float S2, float K, const float* P_mkt, const float* f_mkt, int32_t n_steps_S1,
+                             float* vega, float* sim_ms)
+{
+    HW_TRY(require_model(e));
+    if (!seeds || !vega || !P_mkt || !f_mkt) return HW1F_ERR_INVALID;
+    HW_CUDA(e, cudaSetDevice(e->device));
+    int32_t n = 0;
+    HW_TRY(resolve_steps(e, S1, n_steps_S1, &n));
+    HW_CUDA(e, e->d_moments.ensure(4 * (size_t)e->p.n_mat * kMaxRuns));
+    HW_TRY(upload_market(e, 0, P_mkt, f_mkt));
+    const ScenDev sc = scen_dev(e, e->p.sigma, e->sig_st, 0);
+    HW_TRY(launch_plans(e, &sc, 1, S1, S2));
+    HW_CUDA(e, cudaEventRecord(e->ev0, e->stream));
+    for (int32_t done = 0; done < n_runs; done += kMaxRuns) {
+        const int nb = (n_runs - done < kMaxRuns) ? (n_runs - done) : kMaxRuns;
+        Launch L;
+        HW_TRY(prepare_launch(e, seeds + done, nb, 0, n_paths, 0, &L));
+        HW_TRY(launch_pathwise(e, L, sc, n, K, e->d_moments.p));
+        std::vector<double> mom(2 * (size_t)nb);
+        HW_TRY(download(e, mom.data(), e->d_moments.p, mom.size() * sizeof(double)));
+        for (int r = 0; r < nb; ++r) vega[done + r] = (float)mom[2 * r] / (float)(int)n_paths;   // src/3:561
+    }
+    HW_CUDA(e, cudaEventRecord(e->ev1, e->stream));
+    HW_CUDA(e, cudaEventSynchronize(e->ev1));
+    if (sim_ms) HW_CUDA(e, cudaEventElapsedTime(sim_ms, e->ev0, e->ev1));
+    return HW1F_OK;
+}
+
+// CV-adjusted price of run_zbc_price (src/3:110-166) from five double moments
+static float zbc_price_cv(const double mom[5], uint64_t n_paths, float P0S2)
+{
+    hw1f_zbc_result r;
+    zbc_algebra(mom, n_paths, P0S2, 0, &r);
+    return r.price_cv;
+}
+
+int hw1f_vega_fd(hw1f_engine* e, hw1f_rng* rng, float S1, float S2, float K, const float* P_mkt, const float* f_mkt,
+                 float eps, int32_t n_steps_S1, hw1f_vega_result* out)
+{
+    HW_TRY(require_model(e));
+    if (!rng || !out || !P_mkt || !f_mkt) return HW1F_ERR_INVALID;
+    HW_REQUIRE(e, 2 * rng->n_paths < (1ull << 31), "the reference's int N_total needs 2*n_paths < 2^31");
+    HW_CUDA(e, cudaSetDevice(e->device));
+    int32_t n = 0;
+    HW_TRY(resolve_steps(e, S1, n_steps_S1, &n));
+    HW_CUDA(e, e->d_moments.ensure(4 * (size_t)e->p.n_mat * kMaxRuns));
+    // run_finite_difference, src/3:400-446: sigma -/+ eps, sig_st and shifted drift per bump;
+    // both bumps read the same market curves and the same normals
+    const float sig_m = e->p.sigma - eps, sig_p = e->p.sigma + eps;
+    std::vector<float> tab(e->p.n_steps);
+    host_shifted_drift_table(e->p, sig_m, e->p.sigma, tab.data());
+    HW_TRY(upload_drift(e, 2, tab.data()));
+    host_shifted_drift_table(e->p, sig_p, e->p.sigma, tab.data());
+    HW_TRY(upload_drift(e, 3, tab.data()));
+    HW_TRY(upload_market(e, 0, P_mkt, f_mkt));
+    HW_TRY(upload_market(e, 1, P_mkt, f_mkt));
+    ScenDev sc[2] = {scen_dev(e, sig_m, host_sig_st(e->p, sig_m), 2), scen_dev(e, sig_p, host_sig_st(e->p, sig_p), 3)};
+    HW_CUDA(e, cudaEventRecord(e->ev0, e->stream));
+    HW_TRY(launch_plans(e, sc, 2, S1, S2));
+    Launch L;
+    HW_TRY(prepare_launch(e, &rng->seed, 1, rng->first_path, rng->n_paths, rng->offset, &L));
+    HW_TRY(launch_zbc(e, L, sc, 2, n, K, e->d_moments.p));
+    HW_CUDA(e, cudaEventRecord(e->ev1, e->stream));
+    double mom[10];
+    HW_TRY(download(e, mom, e->d_moments.p, sizeof(mom)));
+    rng->offset += (uint64_t)n;
+    const float P0S2 = P_mkt[e->p.n_mat - 1];
+    out->n_steps_S1 = n;
+    out->price_minus = zbc_price_cv(mom, rng->n_paths, P0S2);
+    out->price_plus = zbc_price_cv(mom + 5, rng->n_paths, P0S2);
+    out->vega_fd = (out->price_plus - out->price_minus) / (2.0f * eps);   // src/3:443
+    HW_CUDA(e, cudaEventElapsedTime(&out->ms_fd, e->ev0, e->ev1));
+    return HW1F_OK;
+}
+
+int hw1f_vega_fd_recalibrated(hw1f_engine* e, hw1f_rng* rng, float S1, float S2, float K, float eps,
+                              int32_t n_steps_S1, hw1f_vega_result* out)
+{
+    HW_TRY(require_model(e));
+    if (!rng || !out) return HW1F_ERR_INVALID;
+    HW_REQUIRE(e, 2 * rng->n_paths < (1ull << 31), "the reference's int N_total needs 2*n_paths < 2^31");
+    HW_CUDA(e, cudaSetDevice(e->device));
+    if ((rng->offset & 1) || (e->stride & 1)) {
+        e->err = "recalibrated FD needs an even normal offset and an even save stride";
+        return HW1F_ERR_UNSUPPORTED;
+    }
+    int32_t n = 0;
+    HW_TRY(resolve_steps(e, S1, n_steps_S1, &n));
+    const int nm = e->p.n_mat;
+    HW_CUDA(e, e->d_moments.ensure(4 * (size_t)nm * kMaxRuns));
+    HW_CUDA(e, e->d_out.ensure(4 * (size_t)nm));
+    HW_CUDA(e, e->d_mkt.ensure(4 * (size_t)nm));
+    // run_finite_difference_recalibrated, src/3:484-525.  recompute_market_data (src/3:449-482)
+    // re-simulates the curve at sigma -/+ eps with the UNSHIFTED base drift (compute_drift_tables
+    // only changes the sensitivity table) on normals [off, off+N_STEPS); the prices then reuse
+    // normals [off, off+n) with the recalibrated curves, base drift, bumped sig_st and sigma.
+    const float sig_m = e->p.sigma - eps, sig_p = e->p.sigma + eps;
+    ScenDev sc[2] = {scen_dev(e, sig_m, host_sig_st(e->p, sig_m), 0), scen_dev(e, sig_p, host_sig_st(e->p, sig_p), 0)};
+    HW_CUDA(e, cudaEventRecord(e->ev0, e->stream));
+    Launch L;
+    HW_TRY(prepare_launch(e, &rng->seed, 1, rng->first_path, rng->n_paths, rng->offset, &L));
+    HW_TRY(launch_curve(e, L, sc, 2, e->d_moments.p));
+    const float inv_dT = 1.0f / e->spacing;
+    for (int s = 0; s < 2; ++s) {
+        float* dP = e->d_mkt.p + 2 * (size_t)s * nm;
+        curve_epilogue_kernel<<<1, ((nm + 31) / 32) * 32, nm * sizeof(float), e->stream>>>(
+            e->d_moments.p + 2 * (size_t)s * nm, nm, rng->n_paths, inv_dT, dP, dP + nm, nullptr);
+        HW_TRY(check_launch(e, "curve_epilogue_kernel"));
+    }
+    HW_TRY(launch_plans(e, sc, 2, S1, S2));
+    HW_TRY(launch_zbc(e, L, sc, 2, n, K, e->d_moments.p));
+    HW_CUDA(e, cudaEventRecord(e->ev1, e->stream));
+    double mom[10];
+    HW_TRY(download(e, mom, e->d_moments.p, sizeof(mom)));
+    float P0S2[2];
+    for (int s = 0; s < 2; ++s)
+        HW_TRY(download(e, &P0S2[s], e->d_mkt.p + 2 * (size_t)s * nm + (nm - 1), sizeof(float)));
+    rng->offset += (uint64_t)n;   // the reference leaves d_states after run_zbc_price (src/3:509-510)
+    out->n_steps_S1 = n;
+    out->price_minus_recal = zbc_price_cv(mom, rng->n_paths, P0S2[0]);
+    out->price_plus_recal = zbc_price_cv(mom + 5, rng->n_paths, P0S2[1]);
+    out->vega_fd_recal = (out->price_plus_recal - out->price_minus_recal) / (2.0f * eps);   // src/3:513
+    HW_CUDA(e, cudaEventElapsedTime(&out->ms_fd_recal, e->ev0, e->ev1));
+    return HW1F_OK;
+}
+
+int hw1f_vega(hw1f_engine* e, hw1f_rng* rng, float S1, float S2, float K, const float* P_mkt, const float* f_mkt,
+              float eps, int32_t n_steps_S1, hw1f_vega_result* out)
+{
+    HW_TRY(require_model(e));
+    if (!rng || !out) return HW1F_ERR_INVALID;
+    memset(out, 0, sizeof(*out));
+    int32_t n = 0;
+    HW_TRY(resolve_steps(e, S1, n_steps_S1, &n));
+    HW_TRY(hw1f_vega_pathwise(e, rng, S1, S2, K, P_mkt, f_mkt, n, out));     // normals [0,n)
+    HW_TRY(hw1f_vega_fd(e, rng, S1, S2, K, P_mkt, f_mkt, eps, n, out));      // normals [n,2n)
+    HW_TRY(hw1f_vega_fd_recalibrated(e, rng, S1, S2, K, eps, n, out));       // normals [2n,..)
+    return HW1F_OK;
+}
+
+int hw1f_fused_moments(hw1f_engine* e, hw1f_rng*, float, float, float, const float*, const float*, int32_t, double*)
+{
+    if (!e) return HW1F_ERR_INVALID;
+    e->err = "hw1f_fused_moments: not built yet";
+    return HW1F_ERR_UNSUPPORTED;
+}
+
+// ---- sample paths / introspection ---------------------------------------------------------------
+static int run_scalar_kernel(hw1f_engine* e, const hw1f_rng* rng, uint64_t path0, int n_show, float* d_paths,
+                             uint32_t* d_state, uint32_t* d_draws, int n_draws, float* d_normals, int n_normals)
+{
+    Launch L;
+    HW_TRY(prepare_launch(e, &rng->seed, 1, rng->first_path + path0, (uint64_t)n_show, rng->offset, &L));
+    const ScenDev sc = scen_dev(e, e->p.sigma, e->sig_st, 0);
+    HW_CUDA(e, e->d_out.ensure((size_t)e->p.n_steps + 8));
+    // plain (non-duplicated) drift table for the scalar kernel
+    float* d_drift = e->d_out.p;
+    HW_TRY(upload(e, d_drift, e->h_drift.data(), e->p.n_steps * sizeof(float)));
+    const int threads = 32, blocks = (n_show + threads - 1) / threads;
+    sample_paths_kernel<<<blocks, threads, 0, e->stream>>>(L.g, L.seeds, model_dev(e), sc, n_show, L.lead, d_drift,
+                                                           d_paths, d_state, d_draws, n_draws, d_normals, n_normals);
+    return check_launch(e, "sample_paths_kernel");
+}
+
+int hw1f_sample_paths(hw1f_engine* e, const hw1f_rng* rng, int32_t n_show, float* r_paths)
+{
+    HW_TRY(require_model(e));
+    if (!rng || !r_paths) return HW1F_ERR_INVALID;
+    HW_REQUIRE(e, n_show >= 1 && (uint64_t)n_show <= rng->n_paths && n_show <= 65536, "n_show out of range");
+    HW_CUDA(e, cudaSetDevice(e->device));
+    const size_t n = (size_t)n_show * (e->p.n_steps + 1);
+    DevBuf<float> buf;
+    HW_CUDA(e, buf.ensure(n));
+    int s = run_scalar_kernel(e, rng, 0, n_show, buf.p, nullptr, nullptr, 0, nullptr, 0);
+    if (s == HW1F_OK) s = download(e, r_paths, buf.p, n * sizeof(float));
+    buf.release();
+    return s;
+}
+
+int hw1f_debug_rng(hw1f_engine* e, const hw1f_rng* rng, uint64_t path, int32_t n_draws, uint32_t* state6,
+                   uint32_t* draws)
+{
+    HW_TRY(require_model(e));
+    if (!rng || !state6) return HW1F_ERR_INVALID;
+    HW_REQUIRE(e, path < rng->n_paths && n_draws >= 0 && n_draws <= (1 << 20), "path / n_draws out of range");
+    HW_REQUIRE(e, (rng->offset & 1) == 0, "hw1f_debug_rng needs an even normal offset");
+    HW_CUDA(e, cudaSetDevice(e->device));
+    DevBuf<uint32_t> buf;
+    HW_CUDA(e, buf.ensure(6 + (size_t)n_draws));
+    int s = run_scalar_kernel(e, rng, path, 1, nullptr, buf.p, n_draws ? buf.p + 6 : nullptr, n_draws, nullptr, 0);
+    std::vector<uint32_t> host(6 + (size_t)n_draws);
+    if (s == HW1F_OK) s = download(e, host.data(), buf.p, host.size() * sizeof(uint32_t));
+    buf.release();
+    if (s != HW1F_OK) return s;
+    memcpy(state6, host.data(), 6 * sizeof(uint32_t));
+    if (draws && n_draws) memcpy(draws, host.data() + 6, (size_t)n_draws * sizeof(uint32_t));
+    return HW1F_OK;
+}
+
+int hw1f_debug_normals(hw1f_engine* e, const hw1f_rng* rng, uint64_t path, int32_t n, float* out)
+{
+    HW_TRY(require_model(e));
+    if (!rng || !out) return HW1F_ERR_INVALID;
+    HW_REQUIRE(e, path < rng->n_paths && n >= 1 && n <= (1 << 20), "path / n out of range");
+    HW_CUDA(e, cudaSetDevice(e->device));
+    DevBuf<float> buf;
+    HW_CUDA(e, buf.ensure((size_t)n));
+    int s = run_scalar_kernel(e, rng, path, 1, nullptr, nullptr, nullptr, 0, buf.p, n);
+    if (s == HW1F_OK) s = download(e, out, buf.p, (size_t)n * sizeof(float));
+    buf.release();
+    return s;
+}
+
+int hw1f_reduction_bench(hw1f_engine* e, hw1f_rng*, int32_t, float, float, float, const float*, const float*, int32_t,
+                         int32_t, int32_t, float*, float*)
+{
+    if (!e) return HW1F_ERR_INVALID;
+    e->err = "hw1f_reduction_bench: not built yet";
+    return HW1F_ERR_UNSUPPORTED;
+}
+
+// state after curand_init(seed, path, 2*floor(normal_offset/2)) computed on the HOST by the
+// engine's own jump algebra (no GPU needed): state6 = {d, v0..v4}
+int hw1f_host_rng_state(uint64_t seed, uint64_t path, uint64_t normal_offset, uint32_t* state6)
+{
+    if (!state6) return HW1F_ERR_INVALID;
+    const JumpTables& jt = jump_tables();
+    BitVec v;
+    const uint32_t d0 = seed_scramble(seed, v);
+    uint64_t sub = path;
+    for (int k = 0; sub != 0 && k < kNumPow; ++k, sub >>= 1)
+        if (sub & 1) v = jt.seq_pow2[k].apply(v);
+    if (sub != 0) return HW1F_ERR_UNSUPPORTED;
+    const uint64_t draws = 2 * (normal_offset / 2);
+    uint64_t off = draws;
+    for (int k = 0; off != 0 && k < kNumPow; ++k, off >>= 1)
+        if (off & 1) v = jt.step_pow2[k].apply(v);
+    if (off != 0) return HW1F_ERR_UNSUPPORTED;
+    state6[0] = d0 + kWeyl * (uint32_t)draws;
+    for (int w = 0; w < 5; ++w) state6[1 + w] = v[w];
+    return HW1F_OK;
+}
+
+int hw1f_pipe_probe(hw1f_engine* e, int32_t which, int32_t iters, float* ms, double* thread_instr)
+{
+    if (!e || !ms || !thread_instr) return HW1F_ERR_INVALID;
+    HW_REQUIRE(e, which >= 0 && which <= 7 && iters >= 1, "which in [0,7], iters >= 1");
+    HW_CUDA(e, cudaSetDevice(e->device));
+    HW_CUDA(e, e->d_out.ensure(64));
+    const int blocks = e->sm_count * 8, threads = 256;
+    for (int rep = 0; rep < 2; ++rep) {   // first pass warms the instruction cache and clocks
+        HW_CUDA(e, cudaEventRecord(e->ev0, e->stream));
+        switch (which) {
+            case 0: probe_kernel<0><<<blocks, threads, 0, e->stream>>>(iters, 1.0f, 12345u, e->d_out.p); break;
+            case 1: probe_kernel<1><<<blocks, threads, 0, e->stream>>>(iters, 1.0f, 12345u, e->d_out.p); break;
+            case 2: probe_kernel<2><<<blocks, threads, 0, e->stream>>>(iters, 1.0f, 12345u, e->d_out.p); break;
+            case 3: probe_kernel<3><<<blocks, threads, 0, e->stream>>>(iters, 1.0f, 12345u, e->d_out.p); break;
+            case 4: probe_kernel<4><<<blocks, threads, 0, e->stream>>>(iters, 1.0f, 12345u, e->d_out.p); break;
+            case 5: probe_kernel<5><<<blocks, threads, 0, e->stream>>>(iters, 1.0f, 12345u, e->d_out.p); break;
+            case 6: probe_kernel<6><<<blocks, threads, 0, e->stream>>>(iters, 1.0f, 12345u, e->d_out.p); break;
+            default: probe_kernel<7><<<blocks, threads, 0, e->stream>>>(iters, 1.0f, 12345u, e->d_out.p); break;
+        }
+        HW_TRY(check_launch(e, "probe_kernel"));
+        HW_CUDA(e, cudaEventRecord(e->ev1, e->stream));
+        HW_CUDA(e, cudaEventSynchronize(e->ev1));
+    }
+    HW_CUDA(e, cudaEventElapsedTime(ms, e->ev0, e->ev1));
+    // probed instructions per thread (for 4/5: the conversion or the MUFU count; the feeder ops are extra)
+    const double per_thread = (which == 6) ? (double)iters * kProbeUnroll * 29.0
+                                           : (double)iters * kProbeUnroll * kProbeChains;
+    *thread_instr = per_thread * (double)blocks * threads;
+    return HW1F_OK;
+}
+
+int hw1f_launch_count(const hw1f_engine* e, uint64_t* n)
+{
+    if (!e || !n) return HW1F_ERR_INVALID;
+    *n = e->launches;
+    return HW1F_OK;
+}
+
+}  // extern "C"

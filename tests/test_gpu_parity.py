@@ -1,0 +1,230 @@
+"""GPU parity tests proper: the CUDA engine (through the C ABI) against the CPU oracle on the same
+seeded inputs.  Integer RNG work must be bit-exact; floating point follows BASELINE.json's
+north_star tolerance (1e-5 relative for P, theta, ZBC price, beta, vega -- the engine/oracle gap
+here is only the MUFU approximation error, so the tests use tighter bounds where they hold)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+N = 1 << 13
+SEED = 1234
+
+
+@pytest.fixture(scope="module")
+def curve(engine, hw):
+    return engine.bond_curve(hw.Rng(SEED, N))
+
+
+@pytest.fixture(scope="module")
+def curve_ref(oracle):
+    s, q = oracle.bond_curve_sums(SEED, N)
+    P, f = oracle.curve_finalize(s, N)
+    return s, q, P, f
+
+
+# ---------------------------------------------------------------- integer layer: bit-exact
+def test_rng_states_and_draws_bit_exact(engine, hw, oracle, golden_dir):
+    with open(os.path.join(golden_dir, "xorwow_golden.json")) as f:
+        golden = json.load(f)
+    for c in golden["cases"]:
+        if c["offset"] % 2 or c["subsequence"] >= (1 << 40):
+            continue
+        # handle window [subsequence - 3, subsequence + 5) so that hi/lo splitting is exercised
+        first = max(c["subsequence"] - 3, 0)
+        rng = hw.Rng(c["seed"], 8, first_path=first).seek(c["offset"])
+        state, draws = engine.debug_rng(rng, c["subsequence"] - first, 2000)
+        assert int(state[0]) == c["d"] and state[1:].tolist() == c["v"], c
+        assert draws[:8].tolist() == c["draws_head"]
+        assert int(draws[499]) == c["draw_499"] and int(draws[1999]) == c["draw_1999"]
+        assert (draws == oracle.draws(c["seed"], c["subsequence"], c["offset"], 2000)).all()
+
+
+@pytest.mark.parametrize("n_paths,first", [(1, 0), (31, 5), (513, 511), (4096, 0), (100000, 123457), (1 << 20, 0),
+                                            (1 << 20, (1 << 30) - 512)])
+def test_rng_any_geometry(engine, hw, oracle, n_paths, first):
+    """ragged path ranges, unaligned first_path, chunk / hi-matrix boundaries"""
+    rng = hw.Rng(987654321, n_paths, first_path=first)
+    for q in sorted({0, n_paths // 2, n_paths - 1, min(511, n_paths - 1), min(512, n_paths - 1)}):
+        state, draws = engine.debug_rng(rng, q, 12)
+        assert (draws == oracle.draws(987654321, first + q, 0, 12)).all(), (n_paths, first, q)
+
+
+def test_normals_match_device_formula(engine, hw, oracle):
+    """Box-Muller floats: same uint32 inputs, MUFU vs libm in the transform"""
+    for off in (0, 1, 500, 999):
+        got = engine.debug_normals(hw.Rng(SEED, 64).seek(off), 17, 200)
+        ref = oracle.normals(SEED, 17, off, 200)
+        assert np.abs(got - ref).max() < 4e-6, off
+    a = engine.debug_normals(hw.Rng(SEED, 64), 3, 100)
+    b = engine.debug_normals(hw.Rng(SEED, 64).seek(37), 3, 63)
+    assert (a[37:] == b).all()          # odd offsets land on the cached cos value, bit-exact
+
+
+# ---------------------------------------------------------------- Q1
+def test_bond_curve_vs_oracle(curve, curve_ref):
+    s, q, P, f = curve_ref
+    assert curve["P"][0] == 1.0
+    assert np.abs(curve["P"] / P - 1).max() < 1e-6
+    # f = -d ln P / dT: a 1e-7 relative wobble of P becomes ~5e-7 absolute in f
+    assert np.abs(curve["f"] - f).max() < 2e-6
+    n = float(N)
+    se = np.sqrt(np.maximum(q / 4 / n - (s / 2 / n) ** 2, 0) / n)
+    assert np.allclose(curve["P_se"][1:], se[1:], rtol=2e-2, atol=2e-9)
+
+
+def test_bond_curve_deterministic_and_offset(engine, hw, curve):
+    again = engine.bond_curve(hw.Rng(SEED, N))
+    assert (again["P"] == curve["P"]).all() and (again["f"] == curve["f"]).all()   # no atomics: bit-reproducible
+    rng = hw.Rng(SEED, N)
+    engine.bond_curve(rng)
+    assert rng.tell() == 1000
+    second = engine.bond_curve(rng)                      # normals [1000, 2000)
+    assert rng.tell() == 2000 and not (second["P"] == curve["P"]).all()
+
+
+def test_bond_curve_moments_shard_additivity(engine, hw):
+    """sharding by path range is exact: moments([0,N)) == moments([0,a)) + moments([a,N)), ragged a"""
+    import torch
+    full = torch.zeros(202, dtype=torch.float64, device="cuda")
+    a_ = torch.zeros(202, dtype=torch.float64, device="cuda")
+    b_ = torch.zeros(202, dtype=torch.float64, device="cuda")
+    cut = 5000 + 37
+    torch.cuda.synchronize()
+    engine.bond_curve_moments(hw.Rng(SEED, N), full.data_ptr())
+    engine.bond_curve_moments(hw.Rng(SEED, cut), a_.data_ptr())
+    engine.bond_curve_moments(hw.Rng(SEED, N - cut, first_path=cut), b_.data_ptr())
+    engine.synchronize()
+    assert torch.allclose(full, a_ + b_, rtol=1e-9, atol=0)
+    out = engine.bond_curve_finish(full.data_ptr(), N)
+    ref = engine.bond_curve(hw.Rng(SEED, N))
+    assert (out["P"] == ref["P"]).all() and (out["f"] == ref["f"]).all()
+
+
+def test_theta_vs_oracle(engine, oracle, curve):
+    got = engine.theta_calibrate(curve["f"])
+    rec, orig, Ts = oracle.theta(curve["f"])
+    assert (got["T"] == Ts).all() and (got["theta_ref"] == orig).all()
+    assert np.abs(got["theta_rec"] - rec).max() < 1e-6
+    assert got["success"] == bool(np.abs(rec - orig)[::10].max() < 0.01)
+
+
+# ---------------------------------------------------------------- Q2b / Q3
+@pytest.mark.parametrize("n_steps,offset", [(500, 0), (499, 0), (500, 499), (499, 499), (500, 1000), (1, 0), (2, 3)])
+def test_zbc_moments_vs_oracle(engine, hw, oracle, curve, n_steps, offset):
+    rng = hw.Rng(SEED + 54321, N).seek(offset)
+    got = engine.zbc_cv(rng, curve["P"], curve["f"], n_steps_S1=n_steps)
+    assert rng.tell() == offset + n_steps
+    mom = oracle.zbc_moments(SEED + 54321, N, curve["P"], curve["f"], n_steps_S1=n_steps, offset=offset)
+    assert np.allclose(got["mom"], mom, rtol=3e-6), (got["mom"], mom)
+    if n_steps >= 499:
+        ref = oracle.zbc_algebra(got["mom"], 2 * N, float(curve["P"][100]))
+        for k in ("mean_X", "mean_Y", "var_Y", "cov", "beta", "price_cv", "corr", "corr_single"):
+            assert got[k] == pytest.approx(ref[k], rel=1e-6, abs=1e-12), k     # same float32 algebra
+        assert got["ci95_lo"] < got["price_cv_f64"] < got["ci95_hi"]
+
+
+def test_zbc_steps_probe(engine):
+    n = engine.steps_to(5.0)
+    assert n in (499, 500)
+    assert engine.steps_to(10.0) in (999, 1000)
+
+
+def test_vega_pathwise_vs_oracle(engine, hw, oracle, curve):
+    for n_steps, offset in ((500, 0), (499, 1)):
+        got = engine.vega_pathwise(hw.Rng(SEED, N).seek(offset), curve["P"], curve["f"], n_steps_S1=n_steps)
+        s, q = oracle.vega_pathwise_sums(SEED, N, curve["P"], curve["f"], n_steps_S1=n_steps, offset=offset)
+        assert got["vega_pathwise_f64"] == pytest.approx(s / N, rel=5e-6)
+        se = np.sqrt((q / N - (s / N) ** 2) / N)
+        assert got["vega_pathwise_se"] == pytest.approx(se, rel=1e-3)
+
+
+def test_vega_fd_vs_oracle(engine, hw, oracle, curve):
+    """both bumps in one launch == two oracle runs on the same normals with shifted drift tables"""
+    eps, sig = np.float32(0.001), np.float32(0.1)
+    rng = hw.Rng(SEED, N).seek(500)
+    got = engine.vega_fd(rng, curve["P"], curve["f"], eps=float(eps), n_steps_S1=500)
+    assert rng.tell() == 1000
+    prices = []
+    for s_new in (sig - eps, sig + eps):
+        drift = oracle.shifted_drift_table(float(s_new))
+        assert (drift == engine.drift_table(2, float(s_new))).all()
+        mom = oracle.zbc_moments(SEED, N, curve["P"], curve["f"], n_steps_S1=500, offset=500, sigma=float(s_new),
+                                 drift=drift)
+        prices.append(oracle.zbc_algebra(mom, 2 * N, float(curve["P"][100]))["price_cv"])
+    assert got["price_minus"] == pytest.approx(prices[0], rel=2e-5)
+    assert got["price_plus"] == pytest.approx(prices[1], rel=2e-5)
+    # the difference quotient amplifies price noise by 1/(2 eps) = 500
+    assert got["vega_fd"] == pytest.approx((prices[1] - prices[0]) / (2 * float(eps)), abs=2e-3)
+
+
+def test_vega_fd_recalibrated_vs_oracle(engine, hw, oracle):
+    eps, sig = np.float32(0.001), np.float32(0.1)
+    rng = hw.Rng(SEED, N).seek(1000)
+    got = engine.vega_fd_recalibrated(rng, eps=float(eps), n_steps_S1=500)
+    assert rng.tell() == 1500
+    prices = []
+    for s_new in (sig - eps, sig + eps):
+        sums, _ = oracle.bond_curve_sums(SEED, N, offset=1000, sigma=float(s_new))     # unshifted base drift
+        P, f = oracle.curve_finalize(sums, N)
+        mom = oracle.zbc_moments(SEED, N, P, f, n_steps_S1=500, offset=1000, sigma=float(s_new))
+        prices.append(oracle.zbc_algebra(mom, 2 * N, float(P[100]))["price_cv"])
+    assert got["price_minus_recal"] == pytest.approx(prices[0], rel=5e-5)
+    assert got["price_plus_recal"] == pytest.approx(prices[1], rel=5e-5)
+
+
+def test_vega_sequence_windows(engine, hw, curve):
+    """hw1f_vega walks the reference's draw windows: [0,n) pathwise, [n,2n) FD, [2n,..) recalibrated"""
+    rng = hw.Rng(SEED, N)
+    allres = engine.vega(rng, curve["P"], curve["f"], n_steps_S1=500)
+    assert rng.tell() == 1500
+    pw = engine.vega_pathwise(hw.Rng(SEED, N), curve["P"], curve["f"], n_steps_S1=500)
+    fd = engine.vega_fd(hw.Rng(SEED, N).seek(500), curve["P"], curve["f"], n_steps_S1=500)
+    rc = engine.vega_fd_recalibrated(hw.Rng(SEED, N).seek(1000), n_steps_S1=500)
+    assert allres["vega_pathwise"] == pw["vega_pathwise"]
+    assert allres["vega_fd"] == fd["vega_fd"] and allres["vega_fd_recal"] == rc["vega_fd_recal"]
+    assert 0.05 < allres["vega_pathwise"] < 0.5 and 0.05 < allres["vega_fd"] < 0.5    # src/3:789-790
+
+
+def test_batches_equal_single_runs(engine, hw, curve):
+    seeds = [1700000000000000 + r * 12345 for r in range(5)]            # src/2:223-229
+    res, _ = engine.zbc_cv_batch(seeds, N, curve["P"], curve["f"], n_steps_S1=500)
+    for s, r in zip(seeds, res):
+        one = engine.zbc_cv(hw.Rng(s, N), curve["P"], curve["f"], n_steps_S1=500)
+        assert r["mom"] == one["mom"] and r["price_cv"] == one["price_cv"]
+    vseeds = [3400000000 + r * 982451653 for r in range(4)]               # src/3:539-545
+    vega, _ = engine.vega_pathwise_batch(vseeds, N, curve["P"], curve["f"], n_steps_S1=500)
+    for s, v in zip(vseeds, vega):
+        assert v == engine.vega_pathwise(hw.Rng(s, N), curve["P"], curve["f"], n_steps_S1=500)["vega_pathwise"]
+
+
+def test_sample_paths_vs_oracle(engine, hw, oracle):
+    rng = hw.Rng(SEED, N).seek(1000)                    # the reference dumps draws 1000..1999 (src/1:163)
+    got = engine.sample_paths(rng, 32)
+    ref = oracle.sample_paths(SEED, 32, offset=1000)
+    assert rng.tell() == 1000                           # no write-back (market_data.cuh:159)
+    assert got.shape == (32, 1001) and np.abs(got - ref).max() < 2e-6
+
+
+def test_errors_are_reported_not_fatal(engine, hw, curve):
+    with pytest.raises(hw.HW1FError):
+        engine.zbc_cv(hw.Rng(1, N), curve["P"], curve["f"], n_steps_S1=5000)
+    with pytest.raises(hw.HW1FError):
+        engine.bond_curve(hw.Rng(1, N).seek(1))         # odd offset: documented as unsupported for Q1
+    assert engine.bond_curve(hw.Rng(SEED, N))["P"][0] == 1.0     # engine still usable
+
+
+# ---------------------------------------------------------------- full size: size-independent properties
+def test_full_size_closed_form(engine, hw):
+    n = 1 << 20
+    c = engine.bond_curve(hw.Rng(20240101, n))
+    assert abs(c["P"][50] - 0.947126) < 5 * c["P_se"][50] + 1e-5
+    assert abs(c["P"][100] - 0.859387) < 5 * c["P_se"][100] + 1e-5
+    z = engine.zbc_cv(hw.Rng(20240101 + 54321, n), c["P"], c["f"])
+    assert abs(z["price_cv_f64"] - 0.025255) < 6 * z["se_cv"] + 2e-5
+    assert abs(z["mean_Y"] - c["P"][100]) < 1e-3
+    v = engine.vega_pathwise(hw.Rng(7, n), c["P"], c["f"])
+    assert abs(v["vega_pathwise_f64"] - 0.240) < 5 * v["vega_pathwise_se"] + 2e-3
