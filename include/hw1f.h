@@ -197,8 +197,10 @@ int hw1f_vega_pathwise_batch(hw1f_engine* eng, const uint64_t* seeds, int32_t n_
 /* ---- fused pass (BASELINE.json scaling run) --------------------------------------------- */
 /* One launch: antithetic curve sums on the maturity grid + ZBC/control moments + pathwise-vega
  * tangent (both antithetic twins) evaluated at step n_steps_S1, all on the same normals.
- * d_moments layout: [0,2*n_mat) curve {sum,sumsq}; then 5 ZBC moments; then {sum v, sum v^2}. */
-#define HW1F_FUSED_EXTRA 7
+ * d_moments layout: [0,2*n_mat) curve {sum p0, sum p0^2}; then the 5 ZBC moments; then
+ * {sum (v1+v2), sum (v1+v2)^2, sum v1} with v1/v2 the pathwise vega sample of the +G/-G twin
+ * (sum v1 equals hw1f_vega_pathwise_moments on the same handle position).  Advances rng by n_steps. */
+#define HW1F_FUSED_EXTRA 8
 int hw1f_fused_moments(hw1f_engine* eng, hw1f_rng* rng, float S1, float S2, float K,
                        const float* P_mkt, const float* f_mkt, int32_t n_steps_S1, double* d_moments);
 

@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "hw1f_kernels.cuh"
+#include "hw1f_kernels_extra.cuh"
 #include "hw1f_probe.cuh"
 #include "xorwow_jump.hpp"
 
@@ -71,6 +72,7 @@ struct hw1f_engine {
     // drift tables, duplicated float2: slot 0 base, 1 sensitivity, 2/3 bumped scenarios
     DevBuf<float2> d_drift[4];
     DevBuf<float> d_mkt;                 // [4][n_mat]: P0,f0,P1,f1
+    DevBuf<float> d_center;              // [n_mat] centring constants of the curve accumulation
     DevBuf<BondPlan> d_plans;
     DevBuf<double> d_partials;
     DevBuf<double> d_moments;            // internal moment vector
@@ -368,13 +370,15 @@ ScenDev scen_dev(const hw1f_engine* e, float sigma, float sig_st, int drift_slot
     s.sig_st = sig_st;
     s.drift2 = e->d_drift[drift_slot].p;
     s.sdrift2 = e->d_drift[1].p;
+    s.center = e->d_center.p;
     return s;
 }
 
-size_t smem_curve(const hw1f_engine* e, int nscen, bool with_sq)
+size_t smem_curve(const hw1f_engine* e, int nscen)
 {
-    const int nq = nscen * (with_sq ? 2 : 1) * e->p.n_mat;
-    return (size_t)kWinWords * 4 + (size_t)nscen * (e->p.n_steps / 2) * sizeof(float4) + (size_t)kWarps * nq * sizeof(double);
+    const int nq = nscen * 2 * e->p.n_mat;
+    return (size_t)kWinWords * 4 + (size_t)nscen * (e->p.n_steps / 2) * sizeof(float4) + (size_t)nq * sizeof(double) +
+           (size_t)kWarps * nq * sizeof(float) + (size_t)nscen * e->p.n_mat * sizeof(float);
 }
 
 template <class K>
@@ -391,19 +395,22 @@ int launch_curve(hw1f_engine* e, const Launch& L, const ScenDev* sc, int nscen, 
 {
     const int nq = nscen * 2 * e->p.n_mat;
     HW_CUDA(e, e->d_partials.ensure((size_t)L.n_runs * L.grid_x * nq));
-    const size_t smem = smem_curve(e, nscen, true);
+    const size_t smem = smem_curve(e, nscen);
     const dim3 grid(L.grid_x, L.n_runs);
     if (nscen == 1) {
-        HW_TRY(set_smem(e, bond_curve_kernel<true, 1>, smem));
-        bond_curve_kernel<true, 1><<<grid, kThreads, smem, e->stream>>>(L.g, L.seeds, model_dev(e), sc[0], sc[0],
-                                                                        e->d_partials.p);
+        HW_TRY(set_smem(e, bond_curve_kernel<1>, smem));
+        bond_curve_kernel<1><<<grid, kThreads, smem, e->stream>>>(L.g, L.seeds, model_dev(e), sc[0], sc[0],
+                                                                  e->d_partials.p);
     } else {
-        HW_TRY(set_smem(e, bond_curve_kernel<true, 2>, smem));
-        bond_curve_kernel<true, 2><<<grid, kThreads, smem, e->stream>>>(L.g, L.seeds, model_dev(e), sc[0], sc[1],
-                                                                        e->d_partials.p);
+        HW_TRY(set_smem(e, bond_curve_kernel<2>, smem));
+        bond_curve_kernel<2><<<grid, kThreads, smem, e->stream>>>(L.g, L.seeds, model_dev(e), sc[0], sc[1],
+                                                                  e->d_partials.p);
     }
     HW_TRY(check_launch(e, "bond_curve_kernel"));
-    return reduce_to(e, L.n_runs, L.grid_x, nq, d_moments);
+    reduce_curve_kernel<<<dim3(e->p.n_mat, L.n_runs * nscen), 256, 0, e->stream>>>(
+        e->d_partials.p, (int)L.grid_x, nscen, e->p.n_mat, sc[0].center, sc[nscen > 1 ? 1 : 0].center, L.g.n_paths,
+        d_moments);
+    return check_launch(e, "reduce_curve_kernel");
 }
 
 int launch_zbc(hw1f_engine* e, const Launch& L, const ScenDev* sc, int nscen, int n_steps_S1, float K,
@@ -556,7 +563,7 @@ int hw1f_engine_destroy(hw1f_engine* e)
     cudaStreamSynchronize(e->stream);
     e->d_Jpow2.release(); e->d_W.release(); e->d_U.release();
     for (auto& d : e->d_drift) d.release();
-    e->d_mkt.release(); e->d_plans.release(); e->d_partials.release(); e->d_moments.release();
+    e->d_mkt.release(); e->d_center.release(); e->d_plans.release(); e->d_partials.release(); e->d_moments.release();
     e->d_out.release(); e->d_int.release();
     if (e->h_stage) cudaFreeHost(e->h_stage);
     if (e->ev0) cudaEventDestroy(e->ev0);
@@ -621,6 +628,18 @@ int hw1f_set_model(hw1f_engine* e, const hw1f_params* p)
     e->h_sdrift.assign(p->n_steps, 0.f);
     host_drift_tables(*p, p->sigma, e->h_drift.data(), e->h_sdrift.data());
     e->has_model = true;
+    {   // centring constants: c_m = 2 exp(-I_m) along the noise-free path (any value near p0 works)
+        std::vector<float> cen(p->n_mat, 2.0f);
+        double r = p->r0, I = 0.0;
+        for (int i = 1; i <= p->n_steps; ++i) {
+            const double rn = r * (double)e->exp_adt + (double)e->h_drift[i - 1];
+            I += 0.5 * (r + rn) * (double)e->dt;
+            r = rn;
+            if (i % e->stride == 0 && i / e->stride < p->n_mat) cen[i / e->stride] = (float)(2.0 * exp(-I));
+        }
+        HW_CUDA(e, e->d_center.ensure(p->n_mat));
+        HW_TRY(upload(e, e->d_center.p, cen.data(), cen.size() * sizeof(float)));
+    }
     HW_TRY(upload_drift(e, 0, e->h_drift.data()));
     HW_TRY(upload_drift(e, 1, e->h_sdrift.data()));
     return HW1F_OK;
@@ -1045,11 +1064,36 @@ int hw1f_vega(hw1f_engine* e, hw1f_rng* rng, float S1, float S2, float K, const 
     return HW1F_OK;
 }
 
-int hw1f_fused_moments(hw1f_engine* e, hw1f_rng*, float, float, float, const float*, const float*, int32_t, double*)
+int hw1f_fused_moments(hw1f_engine* e, hw1f_rng* rng, float S1, float S2, float K, const float* P_mkt,
+                       const float* f_mkt, int32_t n_steps_S1, double* d_moments)
 {
-    if (!e) return HW1F_ERR_INVALID;
-    e->err = "hw1f_fused_moments: not built yet";
-    return HW1F_ERR_UNSUPPORTED;
+    HW_TRY(require_model(e));
+    if (!rng || !P_mkt || !f_mkt || !d_moments) return HW1F_ERR_INVALID;
+    HW_CUDA(e, cudaSetDevice(e->device));
+    int32_t n = 0;
+    HW_TRY(resolve_steps(e, S1, n_steps_S1, &n));
+    if ((rng->offset & 1) || (e->stride & 1) || n <= 0 || (n % e->stride) != 0) {
+        e->err = "fused pass needs an even normal offset, an even save stride and n_steps_S1 on the maturity grid";
+        return HW1F_ERR_UNSUPPORTED;
+    }
+    HW_TRY(upload_market(e, 0, P_mkt, f_mkt));
+    const ScenDev sc = scen_dev(e, e->p.sigma, e->sig_st, 0);
+    HW_TRY(launch_plans(e, &sc, 1, S1, S2));
+    Launch L;
+    HW_TRY(prepare_launch(e, &rng->seed, 1, rng->first_path, rng->n_paths, rng->offset, &L));
+    const int nm = e->p.n_mat, nq = 2 * nm + kFusedExtra;
+    HW_CUDA(e, e->d_partials.ensure((size_t)L.grid_x * nq));
+    const size_t smem = (size_t)kWinWords * 4 + (size_t)(e->p.n_steps / 2 + n / 2) * sizeof(float4) +
+                        (size_t)nq * sizeof(double) + (size_t)kWarps * 2 * nm * sizeof(float) + (size_t)nm * sizeof(float);
+    HW_TRY(set_smem(e, fused_kernel, smem));
+    fused_kernel<<<L.grid_x, kThreads, smem, e->stream>>>(L.g, L.seeds, model_dev(e), sc, e->d_plans.p, n, K,
+                                                          e->d_partials.p);
+    HW_TRY(check_launch(e, "fused_kernel"));
+    HW_TRY(reduce_to(e, 1, L.grid_x, nq, d_moments));
+    fused_uncenter_kernel<<<1, ((nm + 31) / 32) * 32, 0, e->stream>>>(d_moments, nm, sc.center, rng->n_paths);
+    HW_TRY(check_launch(e, "fused_uncenter_kernel"));
+    rng->offset += (uint64_t)e->p.n_steps;
+    return HW1F_OK;
 }
 
 // ---- sample paths / introspection ---------------------------------------------------------------
@@ -1118,12 +1162,65 @@ int hw1f_debug_normals(hw1f_engine* e, const hw1f_rng* rng, uint64_t path, int32
     return s;
 }
 
-int hw1f_reduction_bench(hw1f_engine* e, hw1f_rng*, int32_t, float, float, float, const float*, const float*, int32_t,
-                         int32_t, int32_t, float*, float*)
+int hw1f_reduction_bench(hw1f_engine* e, hw1f_rng* rng, int32_t method, float S1, float S2, float K,
+                         const float* P_mkt, const float* f_mkt, int32_t n_steps_S1, int32_t n_warmup, int32_t n_runs,
+                         float* avg_ms, float* price)
 {
-    if (!e) return HW1F_ERR_INVALID;
-    e->err = "hw1f_reduction_bench: not built yet";
-    return HW1F_ERR_UNSUPPORTED;
+    HW_TRY(require_model(e));
+    if (!rng || !P_mkt || !f_mkt || !avg_ms || !price) return HW1F_ERR_INVALID;
+    HW_REQUIRE(e, method >= 0 && method <= 3 && n_runs >= 1 && n_warmup >= 0, "method in [0,3], n_runs >= 1");
+    HW_CUDA(e, cudaSetDevice(e->device));
+    int32_t n = 0;
+    HW_TRY(resolve_steps(e, S1, n_steps_S1, &n));
+    HW_TRY(upload_market(e, 0, P_mkt, f_mkt));
+    const ScenDev sc = scen_dev(e, e->p.sigma, e->sig_st, 0);
+    HW_TRY(launch_plans(e, &sc, 1, S1, S2));
+    HW_CUDA(e, e->d_moments.ensure(4 * (size_t)e->p.n_mat * kMaxRuns));
+    HW_CUDA(e, e->d_out.ensure(64));
+    float* d_sum = e->d_out.p;
+    const size_t smem = (size_t)kWinWords * 4 + (size_t)((n + 1) / 2 + 1) * sizeof(float4);
+    HW_TRY(set_smem(e, zbc_sum_kernel<0>, smem));
+    HW_TRY(set_smem(e, zbc_sum_kernel<1>, smem));
+    HW_TRY(set_smem(e, zbc_sum_kernel<2>, smem));
+    HW_TRY(set_smem(e, zbc_sum_kernel<3>, smem));
+    double total_ms = 0.0;
+    // benchmark_kernel(), src/benchmark_reductions.cu:34-54: warm-ups then timed launches, each launch
+    // continues the streams (states are written back there; the handle offset advances here)
+    for (int it = 0; it < n_warmup + n_runs; ++it) {
+        Launch L;
+        HW_CUDA(e, cudaMemsetAsync(d_sum, 0, sizeof(float), e->stream));
+        HW_CUDA(e, cudaEventRecord(e->ev0, e->stream));
+        HW_TRY(prepare_launch(e, &rng->seed, 1, rng->first_path, rng->n_paths, rng->offset, &L));
+        HW_CUDA(e, e->d_partials.ensure((size_t)L.grid_x));
+        const ModelDev md = model_dev(e);
+        switch (method) {
+            case 0: zbc_sum_kernel<0><<<L.grid_x, kThreads, smem, e->stream>>>(L.g, L.seeds, md, sc, e->d_plans.p, n, L.lead, K, d_sum, e->d_partials.p); break;
+            case 1: zbc_sum_kernel<1><<<L.grid_x, kThreads, smem, e->stream>>>(L.g, L.seeds, md, sc, e->d_plans.p, n, L.lead, K, d_sum, e->d_partials.p); break;
+            case 2: zbc_sum_kernel<2><<<L.grid_x, kThreads, smem, e->stream>>>(L.g, L.seeds, md, sc, e->d_plans.p, n, L.lead, K, d_sum, e->d_partials.p); break;
+            default: zbc_sum_kernel<3><<<L.grid_x, kThreads, smem, e->stream>>>(L.g, L.seeds, md, sc, e->d_plans.p, n, L.lead, K, d_sum, e->d_partials.p); break;
+        }
+        HW_TRY(check_launch(e, "zbc_sum_kernel"));
+        if (method == 3) HW_TRY(reduce_to(e, 1, L.grid_x, 1, e->d_moments.p));
+        HW_CUDA(e, cudaEventRecord(e->ev1, e->stream));
+        HW_CUDA(e, cudaEventSynchronize(e->ev1));
+        rng->offset += (uint64_t)n;
+        if (it >= n_warmup) {
+            float ms = 0.f;
+            HW_CUDA(e, cudaEventElapsedTime(&ms, e->ev0, e->ev1));
+            total_ms += ms;
+        }
+    }
+    *avg_ms = (float)(total_ms / n_runs);
+    if (method == 3) {
+        double s = 0.0;
+        HW_TRY(download(e, &s, e->d_moments.p, sizeof(double)));
+        *price = (float)s / (2.0f * (float)rng->n_paths);       // h_sum / (2.0f * N_PATHS), src/bench:62
+    } else {
+        float s = 0.f;
+        HW_TRY(download(e, &s, d_sum, sizeof(float)));
+        *price = s / (2.0f * (float)rng->n_paths);
+    }
+    return HW1F_OK;
 }
 
 // state after curand_init(seed, path, 2*floor(normal_offset/2)) computed on the HOST by the

@@ -39,6 +39,7 @@ __device__ __forceinline__ float2 splat(float x) { return make_float2(x, x); }
 
 constexpr float kLog2e = 1.4426950216293334961f;   // expf(x)  -> ex2(x * kLog2e)
 constexpr float kLn2 = 0.69314718246459960938f;    // logf(x)  -> lg2(x) * kLn2
+constexpr float kNeg2Ln2 = -2.0f * kLn2;             // exact: power-of-two scaling of kLn2
 constexpr uint32_t kWeyl = 362437u;                // curand_kernel.h:872
 
 // ---- XORWOW ---------------------------------------------------------------------------------
@@ -77,9 +78,10 @@ __device__ __forceinline__ void box_muller2(uint32_t xa, uint32_t ya, uint32_t x
     const float2 fy = make_float2(u2f(ya), u2f(yb));
     const float2 u = fma2(fx, splat(__uint_as_float(0x2f800000u)), splat(__uint_as_float(0x2f000000u)));
     const float2 v = fma2(fy, splat(__uint_as_float(0x30c90fdbu)), splat(__uint_as_float(0x30490fdbu)));
+    // reference: (lg2(u) * ln2) * -2  ->  one FMUL2 by (-2 ln2): scaling by -2 is exact, so
+    // RN(RN(l*c) * -2) == RN(l * (-2c)) bit for bit (no subnormals can occur: |l*c| >= 5.9e-8 or 0)
     float2 l = make_float2(mufu_lg2(u.x), mufu_lg2(u.y));
-    l = mul2(l, splat(kLn2));
-    l = mul2(l, splat(-2.0f));
+    l = mul2(l, splat(kNeg2Ln2));
     const float2 s = make_float2(mufu_sqrt(l.x), mufu_sqrt(l.y));
     const float2 sn = make_float2(mufu_sin(v.x), mufu_sin(v.y));
     const float2 cs = make_float2(mufu_cos(v.x), mufu_cos(v.y));
@@ -97,12 +99,14 @@ __device__ __forceinline__ void box_muller1(uint32_t x, uint32_t y, float& n_sin
     n_cos = mul_(s, mufu_cos(v));
 }
 
-// evolve_hull_white_step (common.cuh:237-244) for two paths: FFMA2, FADD2, FMUL2, FFMA2
-__device__ __forceinline__ void hw_step2(float2& r, float2& integral, float2 shock, float2 e2, float2 dt2)
+// evolve_hull_white_step (common.cuh:237-244) for two paths.  Reference sequence per path:
+// FFMA (r'), FADD (r+r'), FMUL (*0.5), FFMA (*dt + I).  The halving is exact, so folding it into
+// the constant (hdt = 0.5*dt, also exact) leaves the single rounding of the last FFMA unchanged:
+// FFMA2, FADD2, FFMA2 -- three issue slots for two paths.
+__device__ __forceinline__ void hw_step2(float2& r, float2& integral, float2 shock, float2 e2, float2 hdt2)
 {
     const float2 rn = fma2(r, e2, shock);
-    const float2 h = mul2(add2(rn, r), splat(0.5f));
-    integral = fma2(h, dt2, integral);
+    integral = fma2(add2(rn, r), hdt2, integral);
     r = rn;
 }
 __device__ __forceinline__ void hw_step1(float& r, float& integral, float shock, float e, float dt)
@@ -160,6 +164,19 @@ __device__ __forceinline__ float warp_sum(float x)
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) x = add_(x, __shfl_xor_sync(0xffffffffu, x, o));
     return x;
+}
+// sums two values over the warp with 5 shuffles instead of 10: after the first exchange the
+// lower half-warp carries partial sums of `a`, the upper half those of `b`.
+// Returns the total of a in lanes 0..15 and the total of b in lanes 16..31 (fixed order).
+__device__ __forceinline__ float warp_sum_pair(float a, float b, int lane)
+{
+    const bool up = (lane & 16) != 0;
+    const float give = up ? a : b;
+    float keep = up ? b : a;
+    keep = add_(keep, __shfl_xor_sync(0xffffffffu, give, 16));
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) keep = add_(keep, __shfl_xor_sync(0xffffffffu, keep, o));
+    return keep;
 }
 __device__ __forceinline__ double warp_sum(double x)
 {

@@ -52,6 +52,7 @@ struct ScenDev {
     float sigma, sig_st;
     const float2* drift2;    // duplicated (d,d) drift table in global memory
     const float2* sdrift2;   // duplicated sensitivity drift table (pathwise only)
+    const float* center;     // [n_mat] centring constants c_m of the curve accumulation (Q1 only)
 };
 
 // path-independent pieces of P(S1,S2) = A exp(-B r) and of the pathwise tangent, computed ON
@@ -211,7 +212,11 @@ __device__ __forceinline__ ThreadStreams derive_streams(const StreamGeom& g, con
     const unsigned long long pA = base + tid, pB = pA + kThreads;
     t.validA = (pA >= g.first_path) && (pA < g.first_path + g.n_paths);
     t.validB = (pB >= g.first_path) && (pB < g.first_path + g.n_paths);
-    t.dcur = seeds.s[run].d_start;
+    // keep the Weyl word in a vector register: xorshift + Weyl + immediate is then ONE IADD3 per
+    // draw instead of a uniform-datapath add plus a vector add
+    // (bit 63 of a path index is always 0; the dependence on pA only defeats uniform-register
+    // allocation of this loop-carried value)
+    t.dcur = seeds.s[run].d_start + (uint32_t)(pA >> 63);
     return t;
 }
 
@@ -255,20 +260,25 @@ __device__ __forceinline__ void one_pair(ThreadStreams& t, float2& ns, float2& n
 // =================================================================================================
 // Q1: antithetic bond curve (simulate_zcb, market_data.cuh:25-79)
 // =================================================================================================
-// partials[run][block][nq] doubles, nq = NSCEN * (WITH_SQ ? 2 : 1) * n_mat: sum_m p0, sum_m p0^2.
-// Blocks stride over chunks; per-warp float shuffle trees feed double accumulators in shared memory.
-template <bool WITH_SQ, int NSCEN>
+// partials[run][block][nq] doubles, nq = NSCEN * 2 * n_mat: per scenario sum_m d, sum_m d^2 with
+// d = p0_m - c_m.  Centring (c_m = the noise-free value, host-computed) makes the float shuffle
+// trees lose nothing: the variance of p0 at short maturities is 1e-10 of its square and would
+// vanish in float32 otherwise.  reduce_curve_kernel undoes the centring in double.
+// Blocks stride over chunks; per-warp float trees -> shared floats -> double block accumulators.
+template <int NSCEN>
 __global__ void __launch_bounds__(kThreads, (NSCEN > 1 ? 2 : 4))
 bond_curve_kernel(StreamGeom g, SeedArgs seeds, ModelDev md, ScenDev sc0, ScenDev sc1, double* __restrict__ partials)
 {
     extern __shared__ __align__(16) uint32_t smem[];
     const int n_steps = md.n_steps, n_mat = md.n_mat;
-    const int nq1 = (WITH_SQ ? 2 : 1) * n_mat;   // per scenario
+    const int nq1 = 2 * n_mat;   // per scenario
     const int nq = nq1 * NSCEN;
     const int n_pairs_tot = n_steps >> 1;
     uint32_t* win = smem;
-    float4* drift4 = reinterpret_cast<float4*>(smem + kWinWords);              // [NSCEN][n_steps/2] (d_i,d_i,d_i+1,d_i+1)
-    double* wpart = reinterpret_cast<double*>(drift4 + (size_t)NSCEN * n_pairs_tot);  // [kWarps][nq]
+    float4* drift4 = reinterpret_cast<float4*>(smem + kWinWords);                   // [NSCEN][n_steps/2] (d_i,d_i,d_i+1,d_i+1)
+    double* bacc = reinterpret_cast<double*>(drift4 + (size_t)NSCEN * n_pairs_tot);  // [nq] block accumulators
+    float* wflt = reinterpret_cast<float*>(bacc + nq);                              // [kWarps][nq] this chunk
+    float* cen = wflt + kWarps * nq;                                                // [NSCEN][n_mat]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int run = blockIdx.y;
 
@@ -276,7 +286,12 @@ bond_curve_kernel(StreamGeom g, SeedArgs seeds, ModelDev md, ScenDev sc0, ScenDe
         drift4[i] = reinterpret_cast<const float4*>(sc0.drift2)[i];
         if (NSCEN > 1) drift4[n_pairs_tot + i] = reinterpret_cast<const float4*>(sc1.drift2)[i];
     }
-    for (int k = tid; k < kWarps * nq; k += kThreads) wpart[k] = 0.0;
+    for (int k = tid; k < nq; k += kThreads) bacc[k] = 0.0;
+    for (int k = tid; k < kWarps * nq; k += kThreads) wflt[k] = 0.0f;
+    for (int k = tid; k < n_mat; k += kThreads) {
+        cen[k] = sc0.center[k];
+        if (NSCEN > 1) cen[n_mat + k] = sc1.center[k];
+    }
 
     float2 sgP[NSCEN], sgM[NSCEN];
 #pragma unroll
@@ -285,8 +300,11 @@ bond_curve_kernel(StreamGeom g, SeedArgs seeds, ModelDev md, ScenDev sc0, ScenDe
         sgP[s] = splat(sg);
         sgM[s] = splat(-sg);
     }
-    const float2 e2 = splat(md.exp_adt), dt2 = splat(md.dt);
+    const float2 e2 = splat(md.exp_adt), hdt2 = splat(mul_(0.5f, md.dt));
     const int half = md.stride >> 1;
+    // lane 0 stores the sum, lane 16 the sum of squares (see warp_sum_pair)
+    const bool writer = (lane & 15) == 0;
+    const int woff = warp * nq + ((lane & 16) ? n_mat : 0);
 
     for (unsigned long long chunk = blockIdx.x; chunk < g.n_chunks; chunk += gridDim.x) {
         ThreadStreams t = derive_streams(g, seeds, run, chunk, win);   // contains the __syncthreads()
@@ -304,10 +322,10 @@ bond_curve_kernel(StreamGeom g, SeedArgs seeds, ModelDev md, ScenDev sc0, ScenDe
             for (int s = 0; s < NSCEN; ++s) {
                 const float4 d = drift4[s * n_pairs_tot + pk];
                 const float2 da = make_float2(d.x, d.y), db = make_float2(d.z, d.w);
-                hw_step2(r1[s], I1[s], fma2(ns, sgP[s], da), e2, dt2);
-                hw_step2(r2[s], I2[s], fma2(ns, sgM[s], da), e2, dt2);
-                hw_step2(r1[s], I1[s], fma2(nc, sgP[s], db), e2, dt2);
-                hw_step2(r2[s], I2[s], fma2(nc, sgM[s], db), e2, dt2);
+                hw_step2(r1[s], I1[s], fma2(ns, sgP[s], da), e2, hdt2);
+                hw_step2(r2[s], I2[s], fma2(ns, sgM[s], da), e2, hdt2);
+                hw_step2(r1[s], I1[s], fma2(nc, sgP[s], db), e2, hdt2);
+                hw_step2(r2[s], I2[s], fma2(nc, sgM[s], db), e2, hdt2);
             }
         };
 
@@ -318,26 +336,25 @@ bond_curve_kernel(StreamGeom g, SeedArgs seeds, ModelDev md, ScenDev sc0, ScenDe
             for (int s = 0; s < NSCEN; ++s) {
                 // p0_m = expf(-integral1) + expf(-integral2)   (market_data.cuh:60)
                 const float2 a = mul2(I1[s], splat(-kLog2e)), b = mul2(I2[s], splat(-kLog2e));
-                float2 p0 = add2(make_float2(mufu_ex2(a.x), mufu_ex2(a.y)),
-                                 make_float2(mufu_ex2(b.x), mufu_ex2(b.y)));
-                if (!full) { p0.x = mul_(p0.x, mA); p0.y = mul_(p0.y, mB); }
-                const float sum = warp_sum(add_(p0.x, p0.y));
-                if (lane == 0) wpart[warp * nq + s * nq1 + m] += (double)sum;
-                if (WITH_SQ) {
-                    const float sq = warp_sum(fma_(p0.x, p0.x, mul_(p0.y, p0.y)));
-                    if (lane == 0) wpart[warp * nq + s * nq1 + n_mat + m] += (double)sq;
-                }
+                const float2 p0 = add2(make_float2(mufu_ex2(a.x), mufu_ex2(a.y)),
+                                       make_float2(mufu_ex2(b.x), mufu_ex2(b.y)));
+                float2 dv = add2(p0, splat(-cen[s * n_mat + m]));
+                if (!full) dv = mul2(dv, make_float2(mA, mB));   // block-uniform branch: ragged edge chunks only
+                const float keep = warp_sum_pair(add_(dv.x, dv.y), fma_(dv.x, dv.x, mul_(dv.y, dv.y)), lane);
+                if (writer) wflt[woff + s * nq1 + m] = keep;
             }
+        }
+        __syncthreads();
+        for (int k = tid; k < nq; k += kThreads) {
+            double acc = (double)wflt[k];
+#pragma unroll
+            for (int w = 1; w < kWarps; ++w) acc += (double)wflt[w * nq + k];
+            bacc[k] += acc;
         }
     }
     __syncthreads();
     double* out = partials + ((size_t)run * gridDim.x + blockIdx.x) * nq;
-    for (int k = tid; k < nq; k += kThreads) {
-        double acc = wpart[k];
-#pragma unroll
-        for (int w = 1; w < kWarps; ++w) acc += wpart[w * nq + k];
-        out[k] = acc;
-    }
+    for (int k = tid; k < nq; k += kThreads) out[k] = bacc[k];
 }
 
 // =================================================================================================
@@ -378,7 +395,7 @@ zbc_kernel(StreamGeom g, SeedArgs seeds, ModelDev md, ScenDev sc0, ScenDev sc1, 
         sgP[s] = splat(sg);
         sgM[s] = splat(-sg);
     }
-    const float2 e2 = splat(md.exp_adt), dt2 = splat(md.dt);
+    const float2 e2 = splat(md.exp_adt), hdt2 = splat(mul_(0.5f, md.dt));
 
     for (unsigned long long chunk = blockIdx.x; chunk < g.n_chunks; chunk += gridDim.x) {
         ThreadStreams t = derive_streams(g, seeds, run, chunk, win);
@@ -389,8 +406,8 @@ zbc_kernel(StreamGeom g, SeedArgs seeds, ModelDev md, ScenDev sc0, ScenDev sc1, 
             I1[s] = I2[s] = splat(0.0f);
         }
         auto step1 = [&](int s, float2 d, float2 G) {
-            hw_step2(r1[s], I1[s], fma2(G, sgP[s], d), e2, dt2);
-            hw_step2(r2[s], I2[s], fma2(G, sgM[s], d), e2, dt2);
+            hw_step2(r1[s], I1[s], fma2(G, sgP[s], d), e2, hdt2);
+            hw_step2(r2[s], I2[s], fma2(G, sgM[s], d), e2, hdt2);
         };
         auto pairfn = [&](int pk, float2 ns, float2 nc) {
 #pragma unroll
@@ -476,7 +493,7 @@ pathwise_kernel(StreamGeom g, SeedArgs seeds, ModelDev md, ScenDev sc, const Bon
     }
     if (tid < kWarps * 2) (&wpart[0][0])[tid] = 0.0;
     const BondPlan pl = plans[0];
-    const float2 sg = splat(sc.sig_st), ct = splat(pl.c_t), e2 = splat(md.exp_adt), dt2 = splat(md.dt);
+    const float2 sg = splat(sc.sig_st), ct = splat(pl.c_t), e2 = splat(md.exp_adt), hdt2 = splat(mul_(0.5f, md.dt));
     const int n_main = n_steps_S1 - lead;
 
     for (unsigned long long chunk = blockIdx.x; chunk < g.n_chunks; chunk += gridDim.x) {
@@ -484,8 +501,8 @@ pathwise_kernel(StreamGeom g, SeedArgs seeds, ModelDev md, ScenDev sc, const Bon
         float2 r = splat(md.r0), tg = splat(0.0f), Ir = splat(0.0f), It = splat(0.0f);
         auto step1 = [&](int i, float2 G) {
             const float4 d = dd[i];
-            hw_step2(r, Ir, fma2(G, sg, make_float2(d.x, d.y)), e2, dt2);
-            hw_step2(tg, It, fma2(ct, G, make_float2(d.z, d.w)), e2, dt2);
+            hw_step2(r, Ir, fma2(G, sg, make_float2(d.x, d.y)), e2, hdt2);
+            hw_step2(tg, It, fma2(ct, G, make_float2(d.z, d.w)), e2, hdt2);
         };
         auto pairfn = [&](int pk, float2 ns, float2 nc) {
             step1(lead + 2 * pk, ns);
@@ -552,6 +569,43 @@ reduce_partials_kernel(const T* __restrict__ partials, int n_blocks, int nq, dou
         __syncthreads();
     }
     if (tid == 0) moments[(size_t)run * nq + q] = sh[0];
+}
+
+// curve variant: block (m, run*NSCEN+s) sums sum_d and sum_d2 of maturity m and undoes the centring:
+//   sum p0 = sum d + n c,   sum p0^2 = sum d^2 + 2 c sum d + n c^2      (double)
+__global__ void __launch_bounds__(256)
+reduce_curve_kernel(const double* __restrict__ partials, int n_blocks, int nscen, int n_mat,
+                    const float* __restrict__ center0, const float* __restrict__ center1,
+                    unsigned long long n_local, double* __restrict__ moments)
+{
+    __shared__ double sh[2][256];
+    const int m = blockIdx.x, rs = blockIdx.y, tid = threadIdx.x;
+    const int run = rs / nscen, s = rs % nscen;
+    const int nq = nscen * 2 * n_mat;
+    const double* p = partials + (size_t)run * n_blocks * nq + (size_t)s * 2 * n_mat + m;
+    double a = 0.0, b = 0.0;
+    for (int blk = tid; blk < n_blocks; blk += 256) {
+        a += p[(size_t)blk * nq];
+        b += p[(size_t)blk * nq + n_mat];
+    }
+    sh[0][tid] = a;
+    sh[1][tid] = b;
+    __syncthreads();
+#pragma unroll
+    for (int o = 128; o > 0; o >>= 1) {
+        if (tid < o) { sh[0][tid] += sh[0][tid + o]; sh[1][tid] += sh[1][tid + o]; }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        double* out = moments + (size_t)run * nq + (size_t)s * 2 * n_mat;
+        if (m == 0) { out[0] = 0.0; out[n_mat] = 0.0; }
+        else {
+            const double c = (double)(s ? center1 : center0)[m], n = (double)n_local;
+            const double sd = sh[0][0], sdd = sh[1][0];
+            out[m] = sd + n * c;
+            out[n_mat + m] = sdd + 2.0 * c * sd + n * c * c;
+        }
+    }
 }
 
 // =================================================================================================

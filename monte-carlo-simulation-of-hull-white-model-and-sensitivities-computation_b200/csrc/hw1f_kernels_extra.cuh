@@ -1,0 +1,289 @@
+// hw1f_kernels_extra.cuh -- (1) the reduction-strategy benchmark kernels behind
+// hw1f_reduction_bench (the comparison points of include/perf_benchmark.cuh:19-197 re-expressed on
+// this engine's stateless streams, plus the engine's deterministic tree), and (2) the fused
+// curve + ZBC/control + pathwise-tangent pass of the BASELINE.json scaling run.
+#pragma once
+#include "hw1f_kernels.cuh"
+
+namespace hw1f {
+
+// ---- shared: antithetic simulation to S1 for one scenario, both lanes ------------------------------
+struct PairState { float2 r1, r2, I1, I2; };
+
+__device__ __forceinline__ PairState simulate_to_S1(ThreadStreams& t, const float4* __restrict__ drift4,
+                                                    const float2* __restrict__ drift2_gl, int n_steps_S1, int lead,
+                                                    float r0, float sig_st, float2 e2, float2 hdt2)
+{
+    PairState st;
+    st.r1 = st.r2 = splat(r0);
+    st.I1 = st.I2 = splat(0.0f);
+    const float2 sgP = splat(sig_st), sgM = splat(-sig_st);
+    auto step1 = [&](float2 d, float2 G) {
+        hw_step2(st.r1, st.I1, fma2(G, sgP, d), e2, hdt2);
+        hw_step2(st.r2, st.I2, fma2(G, sgM, d), e2, hdt2);
+    };
+    auto pairfn = [&](int pk, float2 ns, float2 nc) {
+        const float4 d = drift4[pk];
+        step1(make_float2(d.x, d.y), ns);
+        step1(make_float2(d.z, d.w), nc);
+    };
+    const int n_main = n_steps_S1 - lead;
+    if (lead && n_steps_S1 > 0) {
+        float2 ns, nc;
+        one_pair(t, ns, nc);
+        step1(drift2_gl[0], nc);
+    }
+    int pair = 0;
+    advance_pairs(t, pair, n_main >> 1, pairfn);
+    if (n_main & 1) {
+        float2 ns, nc;
+        one_pair(t, ns, nc);
+        const float4 d = drift4[pair];
+        step1(make_float2(d.x, d.y), ns);
+    }
+    return st;
+}
+
+// ZBC payoff of both twins of both lanes: x = discount * max(P - K, 0)  (common.cuh:337-353)
+__device__ __forceinline__ void zbc_payoffs(const PairState& st, const BondPlan& pl, float K, float2& x1, float2& x2,
+                                            float2& c1, float2& c2)
+{
+    const float2 z1 = mul2(mul2(st.r1, splat(pl.negB)), splat(kLog2e));
+    const float2 z2 = mul2(mul2(st.r2, splat(pl.negB)), splat(kLog2e));
+    const float2 P1 = mul2(splat(pl.A), make_float2(mufu_ex2(z1.x), mufu_ex2(z1.y)));
+    const float2 P2 = mul2(splat(pl.A), make_float2(mufu_ex2(z2.x), mufu_ex2(z2.y)));
+    const float2 q1 = mul2(st.I1, splat(-kLog2e)), q2 = mul2(st.I2, splat(-kLog2e));
+    const float2 d1 = make_float2(mufu_ex2(q1.x), mufu_ex2(q1.y));
+    const float2 d2 = make_float2(mufu_ex2(q2.x), mufu_ex2(q2.y));
+    c1 = mul2(P1, d1);
+    c2 = mul2(P2, d2);
+    const float2 g1 = add2(P1, splat(-K)), g2 = add2(P2, splat(-K));
+    x1 = mul2(d1, make_float2(fmaxf(0.0f, g1.x), fmaxf(0.0f, g1.y)));
+    x2 = mul2(d2, make_float2(fmaxf(0.0f, g2.x), fmaxf(0.0f, g2.y)));
+}
+
+// =================================================================================================
+// reduction benchmark: sum of ZBC payoffs, four strategies
+// =================================================================================================
+// METHOD 0: one float atomicAdd per reference thread (simulate_ZBC_naive, perf_benchmark.cuh:57)
+// METHOD 1: shared-memory tree + one atomic per block (simulate_ZBC_shared_memory, :118-127)
+// METHOD 2: warp shuffle + block shuffle + one atomic per block (simulate_ZBC_warp_optimized, :183-196)
+// METHOD 3: the engine's deterministic tree: no atomics, double partial per block
+template <int METHOD>
+__global__ void __launch_bounds__(kThreads, 4)
+zbc_sum_kernel(StreamGeom g, SeedArgs seeds, ModelDev md, ScenDev sc, const BondPlan* __restrict__ plans,
+               int n_steps_S1, int lead, float K, float* __restrict__ sum_f, double* __restrict__ partials)
+{
+    extern __shared__ __align__(16) uint32_t smem[];
+    uint32_t* win = smem;
+    const int n_main = n_steps_S1 - lead;
+    const int n_slots = (n_main + 1) >> 1;
+    float4* drift4 = reinterpret_cast<float4*>(smem + kWinWords);
+    __shared__ float s_red[kThreads];
+    __shared__ double s_dbl[kWarps];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < n_slots; i += kThreads) {
+        const int i0 = lead + 2 * i, i1 = i0 + 1;
+        const float2 a = sc.drift2[i0];
+        const float2 b = (i1 < n_steps_S1) ? sc.drift2[i1] : make_float2(0.0f, 0.0f);
+        drift4[i] = make_float4(a.x, a.y, b.x, b.y);
+    }
+    const BondPlan pl = plans[0];
+    const float2 e2 = splat(md.exp_adt), hdt2 = splat(mul_(0.5f, md.dt));
+    double block_acc = 0.0;
+    for (unsigned long long chunk = blockIdx.x; chunk < g.n_chunks; chunk += gridDim.x) {
+        ThreadStreams t = derive_streams(g, seeds, 0, chunk, win);
+        const PairState st = simulate_to_S1(t, drift4, sc.drift2, n_steps_S1, lead, md.r0, sc.sig_st, e2, hdt2);
+        float2 x1, x2, c1, c2;
+        zbc_payoffs(st, pl, K, x1, x2, c1, c2);
+        const float2 x = add2(x1, x2);                         // payoff1 + payoff2 per reference thread
+        const float xa = t.validA ? x.x : 0.0f, xb = t.validB ? x.y : 0.0f;
+        if (METHOD == 0) {
+            if (t.validA) atomicAdd(sum_f, xa);
+            if (t.validB) atomicAdd(sum_f, xb);
+        } else if (METHOD == 1) {
+            __syncthreads();
+            s_red[tid] = add_(xa, xb);
+            __syncthreads();
+            for (int s = kThreads / 2; s > 0; s >>= 1) {
+                if (tid < s) s_red[tid] += s_red[tid + s];
+                __syncthreads();
+            }
+            if (tid == 0) atomicAdd(sum_f, s_red[0]);
+        } else if (METHOD == 2) {
+            float v = add_(xa, xb);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+            __syncthreads();
+            if (lane == 0) s_red[warp] = v;
+            __syncthreads();
+            if (warp == 0) {
+                float w = (lane < kWarps) ? s_red[lane] : 0.0f;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) w += __shfl_down_sync(0xffffffffu, w, o);
+                if (lane == 0) atomicAdd(sum_f, w);
+            }
+        } else {
+            const double w = warp_sum((double)xa + (double)xb);
+            __syncthreads();
+            if (lane == 0) s_dbl[warp] = w;
+            __syncthreads();
+            if (tid == 0) {
+                double acc = s_dbl[0];
+#pragma unroll
+                for (int k = 1; k < kWarps; ++k) acc += s_dbl[k];
+                block_acc += acc;
+            }
+        }
+    }
+    if (METHOD == 3 && tid == 0) partials[blockIdx.x] = block_acc;
+}
+
+// =================================================================================================
+// fused pass: curve sums on the maturity grid + ZBC/control moments + pathwise tangent at S1,
+// all from ONE set of normals (BASELINE.json scaling-run workload)
+// =================================================================================================
+constexpr int kFusedExtra = 8;   // 5 ZBC moments, sum(v1+v2), sum (v1+v2)^2, sum v1
+
+// partials[block][2*n_mat + kFusedExtra] doubles.  Requires even stride, even n_steps_S1 that is a
+// multiple of the stride, even normal offset (checked on the host).
+__global__ void __launch_bounds__(kThreads, 3)
+fused_kernel(StreamGeom g, SeedArgs seeds, ModelDev md, ScenDev sc, const BondPlan* __restrict__ plans,
+             int n_steps_S1, float K, double* __restrict__ partials)
+{
+    extern __shared__ __align__(16) uint32_t smem[];
+    const int n_steps = md.n_steps, n_mat = md.n_mat;
+    const int nq = 2 * n_mat + kFusedExtra;
+    const int n_pairs_tot = n_steps >> 1;
+    uint32_t* win = smem;
+    float4* drift4 = reinterpret_cast<float4*>(smem + kWinWords);                 // [n_steps/2]
+    float4* sdrift4 = drift4 + n_pairs_tot;                                       // [n_steps_S1/2]
+    double* bacc = reinterpret_cast<double*>(sdrift4 + (n_steps_S1 >> 1));        // [nq]
+    float* wflt = reinterpret_cast<float*>(bacc + nq);                            // [kWarps][2*n_mat]
+    float* cen = wflt + kWarps * 2 * n_mat;                                       // [n_mat]
+    __shared__ double wext[kWarps][kFusedExtra];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    for (int i = tid; i < n_pairs_tot; i += kThreads) drift4[i] = reinterpret_cast<const float4*>(sc.drift2)[i];
+    for (int i = tid; i < (n_steps_S1 >> 1); i += kThreads) sdrift4[i] = reinterpret_cast<const float4*>(sc.sdrift2)[i];
+    for (int k = tid; k < nq; k += kThreads) bacc[k] = 0.0;
+    for (int k = tid; k < kWarps * 2 * n_mat; k += kThreads) wflt[k] = 0.0f;
+    for (int k = tid; k < n_mat; k += kThreads) cen[k] = sc.center[k];
+
+    const BondPlan pl = plans[0];
+    const float2 sgP = splat(sc.sig_st), sgM = splat(-sc.sig_st), ctP = splat(pl.c_t), ctM = splat(-pl.c_t);
+    const float2 e2 = splat(md.exp_adt), hdt2 = splat(mul_(0.5f, md.dt));
+    const int half = md.stride >> 1;
+    const int m_S1 = n_steps_S1 / md.stride;          // maturity index reached at S1
+    const bool writer = (lane & 15) == 0;
+    const int woff = warp * 2 * n_mat + ((lane & 16) ? n_mat : 0);
+
+    for (unsigned long long chunk = blockIdx.x; chunk < g.n_chunks; chunk += gridDim.x) {
+        ThreadStreams t = derive_streams(g, seeds, 0, chunk, win);
+        float2 r1 = splat(md.r0), r2 = splat(md.r0), I1 = splat(0.0f), I2 = splat(0.0f);
+        float2 t1 = splat(0.0f), t2 = splat(0.0f), J1 = splat(0.0f), J2 = splat(0.0f);   // tangents and their integrals
+        const float2 mask = make_float2(t.validA ? 1.0f : 0.0f, t.validB ? 1.0f : 0.0f);
+        const bool full = __syncthreads_and(t.validA && t.validB);
+
+        auto pair_tan = [&](int pk, float2 ns, float2 nc) {       // steps up to S1: r and d(r)/d(sigma)
+            const float4 d = drift4[pk], sd = sdrift4[pk];
+            const float2 da = make_float2(d.x, d.y), db = make_float2(d.z, d.w);
+            const float2 sa = make_float2(sd.x, sd.y), sb = make_float2(sd.z, sd.w);
+            hw_step2(r1, I1, fma2(ns, sgP, da), e2, hdt2);
+            hw_step2(r2, I2, fma2(ns, sgM, da), e2, hdt2);
+            hw_step2(t1, J1, fma2(ctP, ns, sa), e2, hdt2);
+            hw_step2(t2, J2, fma2(ctM, ns, sa), e2, hdt2);
+            hw_step2(r1, I1, fma2(nc, sgP, db), e2, hdt2);
+            hw_step2(r2, I2, fma2(nc, sgM, db), e2, hdt2);
+            hw_step2(t1, J1, fma2(ctP, nc, sb), e2, hdt2);
+            hw_step2(t2, J2, fma2(ctM, nc, sb), e2, hdt2);
+        };
+        auto pair_plain = [&](int pk, float2 ns, float2 nc) {     // after S1: curve only
+            const float4 d = drift4[pk];
+            const float2 da = make_float2(d.x, d.y), db = make_float2(d.z, d.w);
+            hw_step2(r1, I1, fma2(ns, sgP, da), e2, hdt2);
+            hw_step2(r2, I2, fma2(ns, sgM, da), e2, hdt2);
+            hw_step2(r1, I1, fma2(nc, sgP, db), e2, hdt2);
+            hw_step2(r2, I2, fma2(nc, sgM, db), e2, hdt2);
+        };
+        auto save_curve = [&](int m) {
+            const float2 a = mul2(I1, splat(-kLog2e)), b = mul2(I2, splat(-kLog2e));
+            const float2 p0 = add2(make_float2(mufu_ex2(a.x), mufu_ex2(a.y)), make_float2(mufu_ex2(b.x), mufu_ex2(b.y)));
+            float2 dv = add2(p0, splat(-cen[m]));
+            if (!full) dv = mul2(dv, mask);
+            const float keep = warp_sum_pair(add_(dv.x, dv.y), fma_(dv.x, dv.x, mul_(dv.y, dv.y)), lane);
+            if (writer) wflt[woff + m] = keep;
+        };
+
+        int pair = 0;
+        for (int m = 1; m <= m_S1; ++m) { advance_pairs(t, pair, half, pair_tan); save_curve(m); }
+        {   // ---- estimators at S1 ----
+            PairState st; st.r1 = r1; st.r2 = r2; st.I1 = I1; st.I2 = I2;
+            float2 x1, x2, c1, c2;
+            zbc_payoffs(st, pl, K, x1, x2, c1, c2);
+            const float2 tX = add2(x1, x2), tY = add2(c1, c2);
+            const float2 tXX = fma2(x1, x1, mul2(x2, x2)), tYY = fma2(c1, c1, mul2(c2, c2));
+            const float2 tXY = fma2(c1, x1, mul2(c2, x2));
+            // pathwise vega of each twin (src/3:64-80): v = 1[P>K] * (-P B (xk B + t)) D - J D (P-K)^+
+            auto vega_of = [&](float2 r, float2 I, float2 tg, float2 J) {
+                const float2 z = mul2(mul2(r, splat(pl.negB)), splat(kLog2e));
+                const float2 P = mul2(splat(pl.A), make_float2(mufu_ex2(z.x), mufu_ex2(z.y)));
+                const float2 q = mul2(I, splat(-kLog2e));
+                const float2 disc = make_float2(mufu_ex2(q.x), mufu_ex2(q.y));
+                const float2 inner = fma2(splat(pl.xk), splat(pl.B), tg);
+                float2 term1 = mul2(disc, mul2(mul2(P, splat(pl.negB)), inner));
+                if (!(P.x > K)) term1.x = 0.0f;
+                if (!(P.y > K)) term1.y = 0.0f;
+                const float2 gk = add2(P, splat(-K));
+                const float2 payoff = make_float2(fmaxf(0.0f, gk.x), fmaxf(0.0f, gk.y));
+                const float2 zz = mul2(disc, J);
+                return fma2(payoff, make_float2(-zz.x, -zz.y), term1);
+            };
+            const float2 v1 = vega_of(r1, I1, t1, J1), v2 = vega_of(r2, I2, t2, J2);
+            const double mA = t.validA ? 1.0 : 0.0, mB = t.validB ? 1.0 : 0.0;
+            const double vsA = (double)v1.x + (double)v2.x, vsB = (double)v1.y + (double)v2.y;
+            const double ext[kFusedExtra] = {
+                (double)tX.x * mA + (double)tX.y * mB, (double)tY.x * mA + (double)tY.y * mB,
+                (double)tXX.x * mA + (double)tXX.y * mB, (double)tYY.x * mA + (double)tYY.y * mB,
+                (double)tXY.x * mA + (double)tXY.y * mB, vsA * mA + vsB * mB, vsA * vsA * mA + vsB * vsB * mB,
+                (double)v1.x * mA + (double)v1.y * mB};
+#pragma unroll
+            for (int k = 0; k < kFusedExtra; ++k) {
+                const double w = warp_sum(ext[k]);
+                if (lane == 0) wext[warp][k] = w;
+            }
+        }
+        for (int m = m_S1 + 1; m < n_mat; ++m) { advance_pairs(t, pair, half, pair_plain); save_curve(m); }
+        __syncthreads();
+        for (int k = tid; k < 2 * n_mat; k += kThreads) {
+            double acc = (double)wflt[k];
+#pragma unroll
+            for (int w = 1; w < kWarps; ++w) acc += (double)wflt[w * 2 * n_mat + k];
+            bacc[k] += acc;
+        }
+        if (tid < kFusedExtra) {
+            double acc = wext[0][tid];
+#pragma unroll
+            for (int w = 1; w < kWarps; ++w) acc += wext[w][tid];
+            bacc[2 * n_mat + tid] += acc;
+        }
+    }
+    __syncthreads();
+    double* out = partials + (size_t)blockIdx.x * nq;
+    for (int k = tid; k < nq; k += kThreads) out[k] = bacc[k];
+}
+
+// un-centres the curve part of the fused moment vector in place (see reduce_curve_kernel)
+__global__ void fused_uncenter_kernel(double* __restrict__ moments, int n_mat, const float* __restrict__ center,
+                                      unsigned long long n_local)
+{
+    const int m = threadIdx.x;
+    if (m >= n_mat) return;
+    if (m == 0) { moments[0] = 0.0; moments[n_mat] = 0.0; return; }
+    const double c = (double)center[m], n = (double)n_local;
+    const double sd = moments[m], sdd = moments[n_mat + m];
+    moments[m] = sd + n * c;
+    moments[n_mat + m] = sdd + 2.0 * c * sd + n * c * c;
+}
+
+}  // namespace hw1f

@@ -46,11 +46,23 @@ def test_reference_rng_states_bit_exact(engine, hw, ref):
         assert int(state[0]) == st["d"] and state[1:].tolist() == st["v"], st
 
 
-def test_reference_curve(mine, ref):
+def test_reference_curve(mine, ref, oracle):
+    """The reference accumulates P_sum[m] with float32 atomics (market_data.cuh:63,73): 1024 block
+    partials of ~2046 are added to a running sum of ~2e6 whose ulp is 0.125.  At short maturities the
+    partials are nearly identical, the rounding is the same at every add, and the error is a BIAS of
+    up to 1024*0.0625/2.1e6 = 3e-5 relative (observed ~1e-5 at T=0.1), far outside its own MC
+    interval; f = -d ln P/dT amplifies it tenfold at T=0.  So: the engine must sit on the
+    double-precision oracle (same paths, same seeds) to 1e-6, and the reference must sit within its
+    own float32-accumulation error bound of both."""
     P, f = np.array(ref["P"], np.float32), np.array(ref["f"], np.float32)
-    assert np.abs(mine["P"] / P - 1).max() < 1e-5
-    # f amplifies dP/P by 1/(2 dT)=5 and the reference sums P in float32 atomics
-    assert np.abs(mine["f"] - f).max() < 1e-5
+    P_orc, f_orc = oracle.bond_curve(SEED, N)            # full size: a few seconds on the box's cores
+    assert np.abs(mine["P"] / P_orc - 1).max() < 1e-6
+    assert np.abs(mine["f"] - f_orc).max() < 2e-6
+    assert np.abs(P / P_orc - 1).max() < 3e-5             # the reference's own float-atomic error
+    assert np.abs(mine["P"] / P - 1).max() < 3e-5
+    assert np.abs(mine["P"][20:] / P[20:] - 1).max() < 1e-5   # dispersed partials: north-star tolerance
+    assert np.abs(mine["f"] - f).max() < 3e-4
+    assert np.abs(mine["f"][20:] - f[20:]).max() < 3e-5
 
 
 def test_reference_theta(engine, mine, ref):
