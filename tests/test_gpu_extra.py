@@ -1,0 +1,153 @@
+"""GPU tests of the wider surface: the fused pass, the reduction benchmark, and the four drop-in
+drivers run end to end next to the reference's own binaries (seeds pinned on both sides)."""
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+N = 1 << 14
+SEED = 4242
+
+
+@pytest.fixture(scope="module")
+def curve(engine, hw):
+    return engine.bond_curve(hw.Rng(SEED, N))
+
+
+def test_fused_equals_separate_passes(engine, hw, curve):
+    """one launch, one set of normals == the three separate estimators on the same window"""
+    import ctypes as C
+    nm = engine.n_mat
+    fused = torch.zeros(2 * nm + 8, dtype=torch.float64, device="cuda")
+    sep_c = torch.zeros(2 * nm, dtype=torch.float64, device="cuda")
+    sep_z = torch.zeros(5, dtype=torch.float64, device="cuda")
+    sep_v = torch.zeros(2, dtype=torch.float64, device="cuda")
+    torch.cuda.synchronize()
+    P, f = np.ascontiguousarray(curve["P"]), np.ascontiguousarray(curve["f"])
+    lib = hw._ffi.load()
+    rng = hw.Rng(SEED, N)
+    st = lib.hw1f_fused_moments(engine._h, rng._h, 5.0, 10.0, engine.K_DEFAULT, P.ctypes.data_as(C.c_void_p),
+                                f.ctypes.data_as(C.c_void_p), 500, C.c_void_p(fused.data_ptr()))
+    assert st == 0, lib.hw1f_last_error(engine._h)
+    assert rng.tell() == 1000
+    engine.bond_curve_moments(hw.Rng(SEED, N), sep_c.data_ptr())
+    engine.zbc_cv_moments(hw.Rng(SEED, N), P, f, sep_z.data_ptr(), n_steps_S1=500)
+    engine.vega_pathwise_moments(hw.Rng(SEED, N), P, f, sep_v.data_ptr(), n_steps_S1=500)
+    engine.synchronize()
+    fused, sep_c, sep_z, sep_v = (t.cpu().numpy() for t in (fused, sep_c, sep_z, sep_v))
+    assert np.allclose(fused[1:nm], sep_c[1:nm], rtol=1e-12) and np.allclose(fused[nm + 1:2 * nm], sep_c[nm + 1:], rtol=1e-10)
+    assert np.allclose(fused[2 * nm:2 * nm + 5], sep_z, rtol=1e-13)
+    assert fused[2 * nm + 7] == pytest.approx(sep_v[0], rel=1e-12)      # +G twin == the non-antithetic pathwise kernel
+    both = fused[2 * nm + 5] / (2 * N)
+    assert abs(both - sep_v[0] / N) < 0.02                              # antithetic twin: same estimand
+
+
+def test_reduction_bench_methods(engine, hw, curve):
+    rng = hw.Rng(SEED, 1 << 18)
+    ref = engine.zbc_cv(hw.Rng(SEED, 1 << 18), curve["P"], curve["f"], n_steps_S1=500)
+    prices = []
+    for method in range(4):
+        r = engine.reduction_bench(rng, method, curve["P"], curve["f"], n_steps_S1=500, n_warmup=1, n_runs=2)
+        assert r["avg_ms"] > 0
+        prices.append(r["price"])
+        assert abs(r["price"] - ref["price_raw"]) < 8 * ref["se_raw"] + 1e-6
+    assert rng.tell() == 4 * 3 * 500
+    # deterministic tree on the same window as zbc_cv reproduces its raw price
+    one = engine.reduction_bench(hw.Rng(SEED, 1 << 18), 3, curve["P"], curve["f"], n_steps_S1=500, n_warmup=0, n_runs=1)
+    assert one["price"] == pytest.approx(ref["price_raw"], rel=1e-6)
+
+
+# ---------------------------------------------------------------- drivers, end to end
+def _run(cmd, cwd, stdin="", env=None):
+    e = dict(os.environ)
+    e.update(env or {})
+    return subprocess.run(cmd, cwd=cwd, input=stdin, text=True, capture_output=True, env=e, timeout=900)
+
+
+@pytest.fixture(scope="module")
+def driver_runs(tmp_path_factory):
+    bins = os.path.join(ROOT, "bin")
+    if not all(os.path.exists(os.path.join(bins, b)) for b in ("q1", "q2", "q3", "benchmark")):
+        pytest.skip("bin/ drivers not built (make all benchmark)")
+    mine = tmp_path_factory.mktemp("mine")
+    os.makedirs(mine / "data")
+    env = {"HW_SEED": "1700000123", "HW_DEVICE": "0"}
+    logs = {}
+    logs["q1"] = _run([os.path.join(bins, "q1")], mine, env=env)
+    logs["q2"] = _run([os.path.join(bins, "q2")], mine, stdin="y\n", env=env)
+    logs["q3"] = _run([os.path.join(bins, "q3")], mine, stdin="n\ny\n", env=env)
+    logs["benchmark"] = _run([os.path.join(bins, "benchmark")], mine, env=env)
+    ref = None
+    refbin = os.path.join(ROOT, "oracle", "_ref")
+    if os.path.exists(os.path.join(refbin, "q1")):
+        ref = tmp_path_factory.mktemp("ref")
+        os.makedirs(ref / "data")
+        renv = {"LD_PRELOAD": os.path.join(refbin, "libfaketime.so"), "HW1F_FAKE_TIME": "1700000123"}
+        for q, stdin in (("q1", ""), ("q2", "y\n"), ("q3", "n\ny\n"), ("benchmark", "")):
+            logs["ref_" + q] = _run([os.path.join(refbin, q)], ref, stdin=stdin, env=renv)
+    return mine, ref, logs
+
+
+def test_drivers_write_the_frozen_schema(driver_runs):
+    mine, ref, logs = driver_runs
+    for q in ("q1", "q2", "q3", "benchmark"):
+        assert logs[q].returncode == 0, logs[q].stdout[-2000:] + logs[q].stderr[-2000:]
+    data = mine / "data"
+    expected = ["P.bin", "f.bin", "r_paths.bin", "q1_results.json", "P_curve.csv", "f_curve.csv", "summary.txt",
+                "q2a_results.json", "theta_comparison.csv", "zbc_bootstrap_optimal.csv", "zbc_statistics_optimal.txt",
+                "q3_results.json", "vega_bootstrap.csv", "vega_statistics.txt", "benchmark_reductions.json"]
+    for name in expected:
+        assert (data / name).exists(), name
+    assert np.fromfile(data / "P.bin", np.float32).shape == (101,)
+    assert np.fromfile(data / "r_paths.bin", np.float32).shape == (32 * 1001,)
+    q1 = json.load(open(data / "q1_results.json"))
+    assert set(q1) == {"task", "timestamp", "parameters", "P", "f", "performance", "validation"}
+    assert set(q1["parameters"]) == {"N_PATHS", "N_STEPS", "N_MAT", "T_FINAL", "a", "sigma", "r0"}
+    assert set(q1["performance"]) == {"simulation_time_ms", "throughput_Mpaths_per_sec"}
+    assert set(q1["validation"]) == {"P_0_0", "P_0_10", "f_0_0"}
+    q2a = json.load(open(data / "q2a_results.json"))
+    assert set(q2a["error_metrics"]) == {"max_error", "success"} and q2a["error_metrics"]["success"] is True
+    q3 = json.load(open(data / "q3_results.json"))
+    assert set(q3["results"]) == {"sensitivity_mc", "sensitivity_fd", "abs_diff"}
+    br = json.load(open(data / "benchmark_reductions.json"))
+    assert len(br["results"]) == 4 and set(br["results"][0]) == {"method", "time_ms", "throughput_Mpaths_per_sec", "price"}
+    assert open(data / "theta_comparison.csv").readline().strip() == "T,theta_original,theta_recovered"
+    assert open(data / "zbc_bootstrap_optimal.csv").readline().strip() == "run,price_adjusted,price_raw,beta_optimal,correlation"
+    assert open(data / "vega_bootstrap.csv").readline().strip() == "run,vega"
+    assert len(open(data / "vega_bootstrap.csv").readlines()) == 21
+
+
+def test_drivers_match_reference_binaries(driver_runs):
+    """the unmodified reference drivers (sm_100 rebuild, time() pinned by LD_PRELOAD) next to ours"""
+    mine, ref, logs = driver_runs
+    if ref is None:
+        pytest.skip("oracle/_ref binaries not built")
+    for q in ("ref_q1", "ref_q2", "ref_q3"):
+        assert logs[q].returncode == 0, logs[q].stdout[-1500:]
+    Pm, Pr = (np.fromfile(d / "data" / "P.bin", np.float32) for d in (mine, ref))
+    fm, fr = (np.fromfile(d / "data" / "f.bin", np.float32) for d in (mine, ref))
+    assert np.abs(Pm / Pr - 1).max() < 3e-5 and np.abs(Pm[20:] / Pr[20:] - 1).max() < 1e-5
+    assert np.abs(fm - fr).max() < 3e-4
+    rm, rr = (np.fromfile(d / "data" / "r_paths.bin", np.float32) for d in (mine, ref))
+    assert np.abs(rm - rr).max() < 2e-6                      # same 32 trajectories, draw window 1000..1999
+    # same schema on both sides
+    for name in ("q1_results.json", "q2a_results.json", "q3_results.json"):
+        a, b = json.load(open(mine / "data" / name)), json.load(open(ref / "data" / name))
+        assert set(a) == set(b), name
+    q3m, q3r = (json.load(open(d / "data" / "q3_results.json"))["results"] for d in (mine, ref))
+    # both drivers consumed P.bin/f.bin of their own q1; vega agrees to the curve difference
+    assert q3m["sensitivity_mc"] == pytest.approx(q3r["sensitivity_mc"], rel=2e-4)
+    assert q3m["sensitivity_fd"] == pytest.approx(q3r["sensitivity_fd"], abs=1e-3)
+    vm = np.loadtxt(mine / "data" / "vega_bootstrap.csv", delimiter=",", skiprows=1)[:, 1]
+    vr = np.loadtxt(ref / "data" / "vega_bootstrap.csv", delimiter=",", skiprows=1)[:, 1]
+    assert np.abs(vm / vr - 1).max() < 2e-4                  # 20 seeds, one launch vs 20x(malloc+init+kernel)
+    zm = np.loadtxt(mine / "data" / "zbc_bootstrap_optimal.csv", delimiter=",", skiprows=1)
+    zr = np.loadtxt(ref / "data" / "zbc_bootstrap_optimal.csv", delimiter=",", skiprows=1)
+    assert np.abs(zm[:, 1] / zr[:, 1] - 1).max() < 1e-4      # CV-adjusted prices
+    assert np.abs(zm[:, 2] / zr[:, 2] - 1).max() < 1e-4      # raw prices
