@@ -25,6 +25,9 @@ constexpr int kChunk = 2 * kThreads;   // subsequences per block
 constexpr int kChunkLog2 = 9;
 constexpr int kMaxRuns = 32;           // seed axis of the batched launches
 constexpr int kMaxScen = 2;            // sigma scenarios sharing one set of normals
+#ifndef HW1F_MIN_BLOCKS
+#define HW1F_MIN_BLOCKS 5              // resident blocks per SM of the single-scenario kernels (48 regs; A/B in profiles/r01_ab_variants.txt)
+#endif
 
 struct SeedBlock {
     uint32_t v0[5];    // T^offset * v0(seed)  (offset jump folded in on the host)
@@ -266,7 +269,7 @@ __device__ __forceinline__ void one_pair(ThreadStreams& t, float2& ns, float2& n
 // vanish in float32 otherwise.  reduce_curve_kernel undoes the centring in double.
 // Blocks stride over chunks; per-warp float trees -> shared floats -> double block accumulators.
 template <int NSCEN>
-__global__ void __launch_bounds__(kThreads, (NSCEN > 1 ? 2 : 4))
+__global__ void __launch_bounds__(kThreads, (NSCEN > 1 ? 2 : HW1F_MIN_BLOCKS))
 bond_curve_kernel(StreamGeom g, SeedArgs seeds, ModelDev md, ScenDev sc0, ScenDev sc1, double* __restrict__ partials)
 {
     extern __shared__ __align__(16) uint32_t smem[];
@@ -364,7 +367,7 @@ bond_curve_kernel(StreamGeom g, SeedArgs seeds, ModelDev md, ScenDev sc0, ScenDe
 // handles any start parity / step count: `lead` = 1 when the launch starts on the cos half of a
 // Box-Muller pair (odd normal offset), partials[run][block][NSCEN*5] doubles
 template <int NSCEN>
-__global__ void __launch_bounds__(kThreads, 4)
+__global__ void __launch_bounds__(kThreads, (NSCEN > 1 ? 4 : HW1F_MIN_BLOCKS))
 zbc_kernel(StreamGeom g, SeedArgs seeds, ModelDev md, ScenDev sc0, ScenDev sc1, const BondPlan* __restrict__ plans,
            int n_steps_S1, int lead, float K, double* __restrict__ partials)
 {
@@ -477,7 +480,7 @@ zbc_kernel(StreamGeom g, SeedArgs seeds, ModelDev md, ScenDev sc0, ScenDev sc1, 
 // Q3 pathwise vega (simulate_sensitivity, src/3:22-96): NOT antithetic; r and d(r)/d(sigma)
 // driven by the same normal.  partials[run][block][2] doubles: sum v, sum v^2
 // =================================================================================================
-__global__ void __launch_bounds__(kThreads, 4)
+__global__ void __launch_bounds__(kThreads, HW1F_MIN_BLOCKS)
 pathwise_kernel(StreamGeom g, SeedArgs seeds, ModelDev md, ScenDev sc, const BondPlan* __restrict__ plans,
                 int n_steps_S1, int lead, float K, double* __restrict__ partials)
 {

@@ -14,7 +14,13 @@
  *   ref_harness bench <q1|q2|q3> <steps> <warmup> <out.json>
  *       steady-state CUDA-event timings of the reference path: kernel only (the reference's own
  *       published metric, src/1:64-71) and "workload" = init_rng + kernel + epilogue + D2H.
+ *   ref_harness workload <q3seq|zbc20|vega20> <steps> <warmup> <out.json>
+ *       wall-clock of the reference's own HOST functions (stdout silenced): q3seq = init_rng +
+ *       run_sensitivity_mc + run_finite_difference + run_finite_difference_recalibrated (main() of
+ *       src/3); zbc20 / vega20 = the 20-run validations of src/2:210-468 and src/3:527-654
+ *       (they write into ./data, so run from a scratch directory).
  */
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -260,8 +266,49 @@ static int do_bench(const char* which, int steps, int warmup, const char* path)
     return 0;
 }
 
+static int do_workload(const char* which, int steps, int warmup, const char* path)
+{
+    curandState* d_states;
+    cudaMalloc(&d_states, N_PATHS * sizeof(curandState));
+    compute_constants();
+    Q1Out q1;
+    run_q1(1234, d_states, &q1);
+    float *d_P_market, *d_f_market;
+    load_market_data_to_device(q1.P, q1.f, &d_P_market, &d_f_market);
+    FILE* keep = fopen(path, "w");
+    if (!keep) die("cannot open output");
+    fflush(stdout);
+    if (!freopen("/dev/null", "w", stdout)) die("freopen");
+    double total = 0;
+    float v0 = 0, v1 = 0, v2 = 0;
+    for (int it = 0; it < warmup + steps; it++) {
+        cudaDeviceSynchronize();
+        const auto t0 = std::chrono::steady_clock::now();
+        if (!strcmp(which, "q3seq")) {
+            init_rng<<<NB, NTPB>>>(d_states, 1000 + it);
+            compute_constants();
+            run_sensitivity_mc(d_P_market, d_f_market, d_states, &v0);
+            run_finite_difference(d_P_market, d_f_market, d_states, &v1);
+            run_finite_difference_recalibrated(d_states, &v2);
+        } else if (!strcmp(which, "zbc20")) {
+            run_zbc_statistical_validation(d_P_market, d_f_market, q1.P[N_MAT - 1]);
+        } else {
+            run_statistical_validation(d_P_market, d_f_market);
+        }
+        cudaDeviceSynchronize();
+        const auto t1 = std::chrono::steady_clock::now();
+        if (it >= warmup) total += std::chrono::duration<double, std::milli>(t1 - t0).count();
+    }
+    ck("workload");
+    fprintf(keep, "{\"workload\": \"%s\", \"steps\": %d, \"warmup\": %d, \"wall_ms_per_step\": %.6f, "
+                  "\"last\": [%.9g, %.9g, %.9g]}\n", which, steps, warmup, total / steps, v0, v1, v2);
+    fclose(keep);
+    return 0;
+}
+
 int main(int argc, char** argv)
 {
+    if (argc >= 6 && !strcmp(argv[1], "workload")) return do_workload(argv[2], atoi(argv[3]), atoi(argv[4]), argv[5]);
     if (argc >= 4 && !strcmp(argv[1], "parity")) return do_parity(strtoul(argv[2], NULL, 10), argv[3]);
     if (argc >= 6 && !strcmp(argv[1], "bench")) return do_bench(argv[2], atoi(argv[3]), atoi(argv[4]), argv[5]);
     fprintf(stderr, "usage: ref_harness parity <seed> <out.json> | bench <q1|q2|q3> <steps> <warmup> <out.json>\n");

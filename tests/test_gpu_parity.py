@@ -234,3 +234,39 @@ def test_full_size_closed_form(engine, hw):
     assert abs(z["mean_Y"] - c["P"][100]) < 1e-3
     v = engine.vega_pathwise(hw.Rng(7, n), c["P"], c["f"])
     assert abs(v["vega_pathwise_f64"] - 0.240) < 5 * v["vega_pathwise_se"] + 2e-3
+
+
+def test_grid_stride_chunks_large_run(engine, hw, curve):
+    """more chunks than resident blocks: blocks stride over chunks and fold them into their double
+    accumulators; the result must equal the sum of shards that each fit in one pass"""
+    import torch
+    n = (1 << 22) + 3                         # 8193 chunks of 512 > the 32*SMs grid cap
+    full = torch.zeros(202, dtype=torch.float64, device="cuda")
+    torch.cuda.synchronize()
+    engine.bond_curve_moments(hw.Rng(99, n), full.data_ptr())
+    acc = torch.zeros(202, dtype=torch.float64, device="cuda")
+    part = torch.zeros(202, dtype=torch.float64, device="cuda")
+    torch.cuda.synchronize()
+    first = 0
+    for k in range(4):
+        cnt = (1 << 20) + (3 if k == 3 else 0)
+        engine.bond_curve_moments(hw.Rng(99, cnt, first_path=first), part.data_ptr())
+        engine.synchronize()
+        acc += part
+        first += cnt
+    assert torch.allclose(full[1:101], acc[1:101], rtol=2e-8, atol=0)
+    assert torch.allclose(full[102:], acc[102:], rtol=2e-7, atol=0)
+    # same for the ZBC moments (double all the way: tight)
+    zf = torch.zeros(5, dtype=torch.float64, device="cuda")
+    za = torch.zeros(5, dtype=torch.float64, device="cuda")
+    zp = torch.zeros(5, dtype=torch.float64, device="cuda")
+    torch.cuda.synchronize()
+    engine.zbc_cv_moments(hw.Rng(99, n), curve["P"], curve["f"], zf.data_ptr(), n_steps_S1=500)
+    first = 0
+    for k in range(4):
+        cnt = (1 << 20) + (3 if k == 3 else 0)
+        engine.zbc_cv_moments(hw.Rng(99, cnt, first_path=first), curve["P"], curve["f"], zp.data_ptr(), n_steps_S1=500)
+        engine.synchronize()
+        za += zp
+        first += cnt
+    assert torch.allclose(zf, za, rtol=1e-12, atol=0)

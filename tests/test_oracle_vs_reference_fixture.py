@@ -1,0 +1,66 @@
+"""Pins the CPU oracle against outputs of the UNMODIFIED reference kernels run on a B200
+(tests/golden/ref_b200_seed20251018.json, captured by `ref_harness parity 20251018` through
+tests/test_reference_gpu.py with HW1F_SAVE_REF set; generator: oracle/ref/ref_harness.cu).
+Integer states must match bit for bit; the float path within the MUFU-vs-libm gap."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+N = 1 << 20
+
+
+@pytest.fixture(scope="module")
+def ref(golden_dir):
+    with open(os.path.join(golden_dir, "ref_b200_seed20251018.json")) as f:
+        return json.load(f)
+
+
+def test_fixture_provenance(ref):
+    assert ref["device"] == "NVIDIA B200" and ref["n_paths"] == N and ref["seed"] == 20251018
+
+
+def test_rng_states_of_real_init_rng(oracle, hw, ref):
+    """curandState words written by the reference's init_rng on the device == oracle == engine host algebra"""
+    for st in ref["states"]:
+        d = oracle.draws(ref["seed"], st["path"], 0, 1)            # forces the same init path
+        host = hw.package.engine.host_rng_state(ref["seed"], st["path"], 0)
+        assert int(host[0]) == st["d"] and host[1:].tolist() == st["v"]
+        # first draw = v4' + d + 362437 with the reference's state: recompute from the fixture
+        v = st["v"]
+        t = (v[0] ^ (v[0] >> 2)) & 0xffffffff
+        v4 = ((v[4] ^ (v[4] << 4)) ^ (t ^ (t << 1))) & 0xffffffff
+        assert int(d[0]) == (v4 + st["d"] + 362437) & 0xffffffff
+
+
+def test_sample_paths_of_real_kernel(oracle, ref):
+    """simulate_paths_show on the device (draws 1000..1999 of paths 0 and 31) vs the oracle: pins the
+    Box-Muller + step float sequence over 1000 consecutive steps"""
+    got = oracle.sample_paths(ref["seed"], 32, offset=1000)
+    assert np.abs(got[0] - np.array(ref["r_path0"], np.float32)).max() < 2e-6
+    assert np.abs(got[31] - np.array(ref["r_path31"], np.float32)).max() < 2e-6
+
+
+def test_theta_of_real_kernel(oracle, ref):
+    rec, orig, _ = oracle.theta(np.array(ref["f"], np.float32))
+    assert np.abs(rec - np.array(ref["theta_rec"], np.float32)).max() < 1e-6
+    assert (orig == np.array(ref["theta_orig"], np.float32)).all()
+
+
+def test_zbc_moments_of_real_kernel(oracle, ref):
+    """full-size (2^20 pairs, ~25 s on 8 cores): the five float-atomic sums of
+    simulate_ZBC_control_variate vs the oracle's double sums"""
+    P, f = np.array(ref["P"], np.float32), np.array(ref["f"], np.float32)
+    mom = oracle.zbc_moments(ref["seed"] + 54321, N, P, f, n_steps_S1=500)
+    assert np.allclose(mom, ref["zbc_moments"], rtol=2e-5)
+    r = oracle.zbc_algebra(mom, 2 * N, float(P[100]))
+    assert r["price_cv"] == pytest.approx(ref["zbc_price_cv"], rel=1e-5)
+    assert r["mean_X"] == pytest.approx(ref["zbc_mean_X"], rel=1e-5)
+    assert r["beta"] == pytest.approx(ref["zbc_beta"], rel=5e-4)
+
+
+def test_pathwise_vega_of_real_kernel(oracle, ref):
+    P, f = np.array(ref["P"], np.float32), np.array(ref["f"], np.float32)
+    s, _ = oracle.vega_pathwise_sums(ref["seed"], N, P, f, n_steps_S1=500)
+    assert s / N == pytest.approx(ref["vega_pathwise"], rel=1e-5)
