@@ -90,7 +90,7 @@ class ClockSampler(threading.Thread):
                 "power_w_max": max(s[3] for s in sel), "samples": len(sel)}
 
 
-def run_reference_arm(args, rank):
+def run_reference_arm(args, rank, real_stdout):
     """the reference's own CUDA implementation of the path (the reference has no CPU path), driven
     by oracle/_ref/ref_harness on GPU 0; falls back to the OpenMP oracle port if it was not built"""
     if rank != 0:
@@ -136,10 +136,19 @@ def run_reference_arm(args, rank):
                      "cpu_baseline": {"value": value, "unit": UNIT, "cores": o.max_threads(), "kind": "port",
                                       "sample": "OpenMP oracle, 2^14 pairs x 1000 steps per step"},
                      "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
-    print(json.dumps(line), flush=True)
+    _emit(line, real_stdout)
+
+
+def _emit(line, real_stdout):
+    os.write(real_stdout, (json.dumps(line) + "\n").encode())
 
 
 def main():
+    # stdout carries exactly ONE JSON line (rank 0): everything libraries print (e.g. NCCL's
+    # version banner) is diverted to stderr while the benchmark runs
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
@@ -155,7 +164,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
 
     if args.impl == "reference":
-        run_reference_arm(args, rank)
+        run_reference_arm(args, rank, real_stdout)
         return
 
     import numpy as np
@@ -315,7 +324,7 @@ def main():
         "check": {"P_0_10": float(last["P"][-1]), "f_0_0": float(last["f"][0])},
         "published_v100_path_steps_per_s": 3.91e11,
     }
-    print(json.dumps(line), flush=True)
+    _emit(line, real_stdout)
     if world > 1:
         dist.destroy_process_group()
 

@@ -270,3 +270,36 @@ def test_grid_stride_chunks_large_run(engine, hw, curve):
         za += zp
         first += cnt
     assert torch.allclose(zf, za, rtol=1e-12, atol=0)
+
+
+@pytest.mark.parametrize("over", [
+    dict(n_steps=200, n_mat=21),                                   # stride 10, short grid
+    dict(n_steps=400, n_mat=101),                                  # stride 4: remainder pairs in the 5-pair unroll
+    dict(n_steps=600, n_mat=51, T_final=6.0),                      # stride 12, dt = 0.01, spacing 0.12
+    dict(a=0.5, sigma=0.2, r0=0.03, theta_a0=0.02, theta_b0=0.001, theta_a1=0.03, theta_b1=-0.0005, theta_break=4.0),
+])
+def test_other_model_parameters(hw, over):
+    """the engine is not specialised to the reference's macros (common.cuh:16-39)"""
+    from oracle_lib import Oracle
+    o = Oracle(**over)
+    eng = hw.Engine(device=0, params=hw.default_params(**over))
+    try:
+        n = 1 << 12
+        c = eng.bond_curve(hw.Rng(31337, n))
+        P, f = o.bond_curve(31337, n)
+        assert np.abs(c["P"] / P - 1).max() < 1e-6 and np.abs(c["f"] - f).max() < 5e-6
+        assert (eng.drift_table(0) == o.drift_tables()[0]).all() and (eng.drift_table(1) == o.drift_tables()[1]).all()
+        th = eng.theta_calibrate(c["f"])
+        assert np.abs(th["theta_rec"] - o.theta(c["f"])[0]).max() < 2e-6
+        S1, S2 = 0.4 * o.p.T_final, 0.8 * o.p.T_final
+        ns = eng.steps_to(S1)
+        assert abs(ns - S1 / o.dt) <= 1
+        K = float(np.float32(0.9) * P[int(round(0.8 * (o.p.n_mat - 1)))] / P[int(round(0.4 * (o.p.n_mat - 1)))])
+        z = eng.zbc_cv(hw.Rng(5, n), c["P"], c["f"], S1=S1, S2=S2, K=K, n_steps_S1=ns)
+        mom = o.zbc_moments(5, n, c["P"], c["f"], S1=S1, S2=S2, K=K, n_steps_S1=ns)
+        assert np.allclose(z["mom"], mom, rtol=5e-6)
+        v = eng.vega_pathwise(hw.Rng(6, n), c["P"], c["f"], S1=S1, S2=S2, K=K, n_steps_S1=ns)
+        s, _ = o.vega_pathwise_sums(6, n, c["P"], c["f"], S1=S1, S2=S2, K=K, n_steps_S1=ns)
+        assert v["vega_pathwise_f64"] == pytest.approx(s / n, rel=2e-5, abs=1e-7)
+    finally:
+        eng.close()
