@@ -203,6 +203,22 @@ int hw1f_vega_pathwise_batch(hw1f_engine* eng, const uint64_t* seeds, int32_t n_
 #define HW1F_FUSED_EXTRA 8
 int hw1f_fused_moments(hw1f_engine* eng, hw1f_rng* rng, float S1, float S2, float K,
                        const float* P_mkt, const float* f_mkt, int32_t n_steps_S1, double* d_moments);
+/* the same pass with the two common-random-number FD bumps sigma -/+ eps of run_finite_difference
+ * (src/3:400-446) riding on the same normals: d_moments gets HW1F_FUSED_FD_EXTRA more doubles
+ * (5 ZBC moments at sigma-eps, 5 at sigma+eps) after the HW1F_FUSED_EXTRA block. */
+#define HW1F_FUSED_FD_EXTRA 10
+int hw1f_fused_fd_moments(hw1f_engine* eng, hw1f_rng* rng, float S1, float S2, float K,
+                          const float* P_mkt, const float* f_mkt, float eps, int32_t n_steps_S1,
+                          double* d_moments);
+/* host-buffer form of the fused pass: ONE launch gives the curve (P, f, P_se), the ZBC price with
+ * control variate (zbc), the antithetic pathwise vega and the CRN finite-difference vega (vega).
+ * "Single-window" mode: every estimator reads normals [offset, offset+n_steps) -- statistically
+ * equivalent to, but not stream-identical with, the reference's q3 (which uses a different draw
+ * window per estimator; hw1f_vega reproduces those).  Advances rng by n_steps. */
+int hw1f_fused(hw1f_engine* eng, hw1f_rng* rng, float S1, float S2, float K,
+               const float* P_mkt, const float* f_mkt, float eps, int32_t n_steps_S1,
+               float* P, float* f, float* P_se, hw1f_zbc_result* zbc, hw1f_vega_result* vega,
+               float* sim_ms);
 
 /* ---- sample trajectories -------------------------------------------------------------- */
 /* simulate_paths_show<<<1,32>>> (market_data.cuh:136-160; src/1:163): r_paths[n_show*(n_steps+1)].

@@ -99,6 +99,9 @@ SYMBOLS = {
     "hw1f_vega_pathwise_batch": (C.c_int, [_P, _P, C.c_int32, C.c_uint64, C.c_float, C.c_float, C.c_float, _P, _P,
                                            C.c_int32, _P, _F]),
     "hw1f_fused_moments": (C.c_int, [_P, _P, C.c_float, C.c_float, C.c_float, _P, _P, C.c_int32, _P]),
+    "hw1f_fused_fd_moments": (C.c_int, [_P, _P, C.c_float, C.c_float, C.c_float, _P, _P, C.c_float, C.c_int32, _P]),
+    "hw1f_fused": (C.c_int, [_P, _P, C.c_float, C.c_float, C.c_float, _P, _P, C.c_float, C.c_int32, _P, _P, _P,
+                             C.POINTER(ZbcResult), C.POINTER(VegaResult), _F]),
     "hw1f_sample_paths": (C.c_int, [_P, _P, C.c_int32, _P]),
     "hw1f_reduction_bench": (C.c_int, [_P, _P, C.c_int32, C.c_float, C.c_float, C.c_float, _P, _P, C.c_int32,
                                        C.c_int32, C.c_int32, _F, _F]),

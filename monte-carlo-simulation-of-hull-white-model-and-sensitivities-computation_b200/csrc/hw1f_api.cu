@@ -1064,8 +1064,8 @@ int hw1f_vega(hw1f_engine* e, hw1f_rng* rng, float S1, float S2, float K, const 
     return HW1F_OK;
 }
 
-int hw1f_fused_moments(hw1f_engine* e, hw1f_rng* rng, float S1, float S2, float K, const float* P_mkt,
-                       const float* f_mkt, int32_t n_steps_S1, double* d_moments)
+static int fused_launch(hw1f_engine* e, hw1f_rng* rng, float S1, float S2, float K, const float* P_mkt,
+                        const float* f_mkt, bool fd, float eps, int32_t n_steps_S1, double* d_moments)
 {
     HW_TRY(require_model(e));
     if (!rng || !P_mkt || !f_mkt || !d_moments) return HW1F_ERR_INVALID;
@@ -1077,22 +1077,99 @@ int hw1f_fused_moments(hw1f_engine* e, hw1f_rng* rng, float S1, float S2, float 
         return HW1F_ERR_UNSUPPORTED;
     }
     HW_TRY(upload_market(e, 0, P_mkt, f_mkt));
-    const ScenDev sc = scen_dev(e, e->p.sigma, e->sig_st, 0);
-    HW_TRY(launch_plans(e, &sc, 1, S1, S2));
+    ScenDev sc[3] = {scen_dev(e, e->p.sigma, e->sig_st, 0), scen_dev(e, e->p.sigma, e->sig_st, 0),
+                     scen_dev(e, e->p.sigma, e->sig_st, 0)};
+    HW_CUDA(e, e->d_plans.ensure(4));
+    HW_TRY(launch_plans(e, sc, 1, S1, S2));
+    if (fd) {   // run_finite_difference's scenarios (src/3:414-435): sigma -/+ eps, shifted drift, same curves
+        const float sig_m = e->p.sigma - eps, sig_p = e->p.sigma + eps;
+        std::vector<float> tab(e->p.n_steps);
+        host_shifted_drift_table(e->p, sig_m, e->p.sigma, tab.data());
+        HW_TRY(upload_drift(e, 2, tab.data()));
+        host_shifted_drift_table(e->p, sig_p, e->p.sigma, tab.data());
+        HW_TRY(upload_drift(e, 3, tab.data()));
+        HW_TRY(upload_market(e, 1, P_mkt, f_mkt));
+        sc[1] = scen_dev(e, sig_m, host_sig_st(e->p, sig_m), 2);
+        sc[2] = scen_dev(e, sig_p, host_sig_st(e->p, sig_p), 3);
+        const int nmk = e->p.n_mat;
+        const float* P0 = e->d_mkt.p;
+        bond_plan_kernel<<<1, 32, 0, e->stream>>>(model_dev(e), sc[1], sc[2], 2, S1, S2, P0, P0 + nmk, P0 + 2 * nmk,
+                                                  P0 + 3 * nmk, e->d_plans.p + 1);
+        HW_TRY(check_launch(e, "bond_plan_kernel"));
+    }
     Launch L;
     HW_TRY(prepare_launch(e, &rng->seed, 1, rng->first_path, rng->n_paths, rng->offset, &L));
-    const int nm = e->p.n_mat, nq = 2 * nm + kFusedExtra;
+    const int nm = e->p.n_mat, next = kFusedExtra + (fd ? kFusedFdExtra : 0), nq = 2 * nm + next;
     HW_CUDA(e, e->d_partials.ensure((size_t)L.grid_x * nq));
-    const size_t smem = (size_t)kWinWords * 4 + (size_t)(e->p.n_steps / 2 + n / 2) * sizeof(float4) +
+    const size_t smem = (size_t)kWinWords * 4 + (size_t)(e->p.n_steps / 2 + (fd ? 3 : 1) * (n / 2)) * sizeof(float4) +
                         (size_t)nq * sizeof(double) + (size_t)kWarps * 2 * nm * sizeof(float) + (size_t)nm * sizeof(float);
-    HW_TRY(set_smem(e, fused_kernel, smem));
-    fused_kernel<<<L.grid_x, kThreads, smem, e->stream>>>(L.g, L.seeds, model_dev(e), sc, e->d_plans.p, n, K,
-                                                          e->d_partials.p);
+    if (fd) {
+        HW_TRY(set_smem(e, fused_kernel<true>, smem));
+        fused_kernel<true><<<L.grid_x, kThreads, smem, e->stream>>>(L.g, L.seeds, model_dev(e), sc[0], sc[1], sc[2],
+                                                                    e->d_plans.p, n, K, e->d_partials.p);
+    } else {
+        HW_TRY(set_smem(e, fused_kernel<false>, smem));
+        fused_kernel<false><<<L.grid_x, kThreads, smem, e->stream>>>(L.g, L.seeds, model_dev(e), sc[0], sc[0], sc[0],
+                                                                     e->d_plans.p, n, K, e->d_partials.p);
+    }
     HW_TRY(check_launch(e, "fused_kernel"));
     HW_TRY(reduce_to(e, 1, L.grid_x, nq, d_moments));
-    fused_uncenter_kernel<<<1, ((nm + 31) / 32) * 32, 0, e->stream>>>(d_moments, nm, sc.center, rng->n_paths);
+    fused_uncenter_kernel<<<1, ((nm + 31) / 32) * 32, 0, e->stream>>>(d_moments, nm, sc[0].center, rng->n_paths);
     HW_TRY(check_launch(e, "fused_uncenter_kernel"));
     rng->offset += (uint64_t)e->p.n_steps;
+    return HW1F_OK;
+}
+
+int hw1f_fused_moments(hw1f_engine* e, hw1f_rng* rng, float S1, float S2, float K, const float* P_mkt,
+                       const float* f_mkt, int32_t n_steps_S1, double* d_moments)
+{
+    if (!e) return HW1F_ERR_INVALID;
+    return fused_launch(e, rng, S1, S2, K, P_mkt, f_mkt, false, 0.0f, n_steps_S1, d_moments);
+}
+
+int hw1f_fused_fd_moments(hw1f_engine* e, hw1f_rng* rng, float S1, float S2, float K, const float* P_mkt,
+                          const float* f_mkt, float eps, int32_t n_steps_S1, double* d_moments)
+{
+    if (!e) return HW1F_ERR_INVALID;
+    HW_REQUIRE(e, eps > 0.0f && eps < e->p.sigma, "eps must be in (0, sigma)");
+    return fused_launch(e, rng, S1, S2, K, P_mkt, f_mkt, true, eps, n_steps_S1, d_moments);
+}
+
+int hw1f_fused(hw1f_engine* e, hw1f_rng* rng, float S1, float S2, float K, const float* P_mkt, const float* f_mkt,
+               float eps, int32_t n_steps_S1, float* P, float* f, float* P_se, hw1f_zbc_result* zbc,
+               hw1f_vega_result* vega, float* sim_ms)
+{
+    HW_TRY(require_model(e));
+    if (!rng || !P || !f || !zbc || !vega) return HW1F_ERR_INVALID;
+    HW_REQUIRE(e, 2 * rng->n_paths < (1ull << 31), "the reference's int N_total needs 2*n_paths < 2^31");
+    HW_CUDA(e, cudaSetDevice(e->device));
+    int32_t n = 0;
+    HW_TRY(resolve_steps(e, S1, n_steps_S1, &n));
+    const int nm = e->p.n_mat, next = kFusedExtra + kFusedFdExtra;
+    HW_CUDA(e, e->d_moments.ensure(4 * (size_t)nm * kMaxRuns));
+    HW_CUDA(e, cudaEventRecord(e->ev0, e->stream));
+    HW_TRY(fused_launch(e, rng, S1, S2, K, P_mkt, f_mkt, true, eps, n, e->d_moments.p));
+    HW_CUDA(e, cudaEventRecord(e->ev1, e->stream));
+    HW_TRY(hw1f_bond_curve_finish(e, e->d_moments.p, rng->n_paths, P, f, P_se));
+    std::vector<double> ext(next);
+    HW_TRY(download(e, ext.data(), e->d_moments.p + 2 * nm, ext.size() * sizeof(double)));
+    const float P0S2 = P_mkt[nm - 1];
+    zbc_algebra(ext.data(), rng->n_paths, P0S2, n, zbc);
+    memset(vega, 0, sizeof(*vega));
+    vega->n_steps_S1 = n;
+    const double np2 = 2.0 * (double)rng->n_paths, np1 = (double)rng->n_paths;
+    vega->vega_pathwise_f64 = ext[5] / np2;                 // both antithetic twins
+    vega->vega_pathwise = (float)vega->vega_pathwise_f64;
+    const double mean_pair = ext[5] / np1;                  // pair sums: var of the pair mean
+    const double var_pair = (np1 > 1) ? (ext[6] - np1 * mean_pair * mean_pair) / (np1 - 1.0) : 0.0;
+    vega->vega_pathwise_se = (var_pair > 0) ? 0.5 * sqrt(var_pair / np1) : 0.0;
+    vega->price_minus = zbc_price_cv(ext.data() + kFusedExtra, rng->n_paths, P0S2);
+    vega->price_plus = zbc_price_cv(ext.data() + kFusedExtra + 5, rng->n_paths, P0S2);
+    vega->vega_fd = (vega->price_plus - vega->price_minus) / (2.0f * eps);
+    float ms = 0.f;
+    HW_CUDA(e, cudaEventElapsedTime(&ms, e->ev0, e->ev1));
+    vega->ms_pathwise = vega->ms_fd = ms;
+    if (sim_ms) *sim_ms = ms;
     return HW1F_OK;
 }
 

@@ -143,29 +143,43 @@ zbc_sum_kernel(StreamGeom g, SeedArgs seeds, ModelDev md, ScenDev sc, const Bond
 // fused pass: curve sums on the maturity grid + ZBC/control moments + pathwise tangent at S1,
 // all from ONE set of normals (BASELINE.json scaling-run workload)
 // =================================================================================================
-constexpr int kFusedExtra = 8;   // 5 ZBC moments, sum(v1+v2), sum (v1+v2)^2, sum v1
+constexpr int kFusedExtra = 8;     // 5 ZBC moments, sum(v1+v2), sum (v1+v2)^2, sum v1
+constexpr int kFusedFdExtra = 10;  // + 5 ZBC moments at sigma-eps and 5 at sigma+eps (FD variant)
 
-// partials[block][2*n_mat + kFusedExtra] doubles.  Requires even stride, even n_steps_S1 that is a
-// multiple of the stride, even normal offset (checked on the host).
-__global__ void __launch_bounds__(kThreads, 3)
-fused_kernel(StreamGeom g, SeedArgs seeds, ModelDev md, ScenDev sc, const BondPlan* __restrict__ plans,
-             int n_steps_S1, float K, double* __restrict__ partials)
+// partials[block][2*n_mat + kFusedExtra (+ kFusedFdExtra)] doubles.  Requires even stride, even
+// n_steps_S1 that is a multiple of the stride, even normal offset (checked on the host).
+// FD = true adds the two bumped-sigma antithetic pairs of run_finite_difference (src/3:400-446) on the
+// SAME normals: scm/scp carry sig_st and the shifted drift tables, plans[1], plans[2] their A(S1,S2).
+template <bool FD>
+__global__ void __launch_bounds__(kThreads, (FD ? 2 : 3))
+fused_kernel(StreamGeom g, SeedArgs seeds, ModelDev md, ScenDev sc, ScenDev scm, ScenDev scp,
+             const BondPlan* __restrict__ plans, int n_steps_S1, float K, double* __restrict__ partials)
 {
     extern __shared__ __align__(16) uint32_t smem[];
     const int n_steps = md.n_steps, n_mat = md.n_mat;
-    const int nq = 2 * n_mat + kFusedExtra;
+    constexpr int kExt = kFusedExtra + (FD ? kFusedFdExtra : 0);
+    const int nq = 2 * n_mat + kExt;
     const int n_pairs_tot = n_steps >> 1;
+    const int n_pairs_S1 = n_steps_S1 >> 1;
     uint32_t* win = smem;
     float4* drift4 = reinterpret_cast<float4*>(smem + kWinWords);                 // [n_steps/2]
     float4* sdrift4 = drift4 + n_pairs_tot;                                       // [n_steps_S1/2]
-    double* bacc = reinterpret_cast<double*>(sdrift4 + (n_steps_S1 >> 1));        // [nq]
+    float4* dm4 = sdrift4 + n_pairs_S1;                                           // [n_steps_S1/2] (FD) sigma-eps drift
+    float4* dp4 = dm4 + (FD ? n_pairs_S1 : 0);                                    // [n_steps_S1/2] (FD) sigma+eps drift
+    double* bacc = reinterpret_cast<double*>(dp4 + (FD ? n_pairs_S1 : 0));        // [nq]
     float* wflt = reinterpret_cast<float*>(bacc + nq);                            // [kWarps][2*n_mat]
     float* cen = wflt + kWarps * 2 * n_mat;                                       // [n_mat]
-    __shared__ double wext[kWarps][kFusedExtra];
+    __shared__ double wext[kWarps][kExt];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     for (int i = tid; i < n_pairs_tot; i += kThreads) drift4[i] = reinterpret_cast<const float4*>(sc.drift2)[i];
-    for (int i = tid; i < (n_steps_S1 >> 1); i += kThreads) sdrift4[i] = reinterpret_cast<const float4*>(sc.sdrift2)[i];
+    for (int i = tid; i < n_pairs_S1; i += kThreads) {
+        sdrift4[i] = reinterpret_cast<const float4*>(sc.sdrift2)[i];
+        if (FD) {
+            dm4[i] = reinterpret_cast<const float4*>(scm.drift2)[i];
+            dp4[i] = reinterpret_cast<const float4*>(scp.drift2)[i];
+        }
+    }
     for (int k = tid; k < nq; k += kThreads) bacc[k] = 0.0;
     for (int k = tid; k < kWarps * 2 * n_mat; k += kThreads) wflt[k] = 0.0f;
     for (int k = tid; k < n_mat; k += kThreads) cen[k] = sc.center[k];
@@ -173,6 +187,7 @@ fused_kernel(StreamGeom g, SeedArgs seeds, ModelDev md, ScenDev sc, const BondPl
     const BondPlan pl = plans[0];
     const float2 sgP = splat(sc.sig_st), sgM = splat(-sc.sig_st), ctP = splat(pl.c_t), ctM = splat(-pl.c_t);
     const float2 e2 = splat(md.exp_adt), hdt2 = splat(mul_(0.5f, md.dt));
+    const float2 smP = splat(scm.sig_st), smM = splat(-scm.sig_st), spP = splat(scp.sig_st), spM = splat(-scp.sig_st);
     const int half = md.stride >> 1;
     const int m_S1 = n_steps_S1 / md.stride;          // maturity index reached at S1
     const bool writer = (lane & 15) == 0;
@@ -182,6 +197,9 @@ fused_kernel(StreamGeom g, SeedArgs seeds, ModelDev md, ScenDev sc, const BondPl
         ThreadStreams t = derive_streams(g, seeds, 0, chunk, win);
         float2 r1 = splat(md.r0), r2 = splat(md.r0), I1 = splat(0.0f), I2 = splat(0.0f);
         float2 t1 = splat(0.0f), t2 = splat(0.0f), J1 = splat(0.0f), J2 = splat(0.0f);   // tangents and their integrals
+        PairState bm, bp;                                                                  // bumped-sigma pairs (FD)
+        bm.r1 = bm.r2 = bp.r1 = bp.r2 = splat(md.r0);
+        bm.I1 = bm.I2 = bp.I1 = bp.I2 = splat(0.0f);
         const float2 mask = make_float2(t.validA ? 1.0f : 0.0f, t.validB ? 1.0f : 0.0f);
         const bool full = __syncthreads_and(t.validA && t.validB);
 
@@ -197,6 +215,19 @@ fused_kernel(StreamGeom g, SeedArgs seeds, ModelDev md, ScenDev sc, const BondPl
             hw_step2(r2, I2, fma2(nc, sgM, db), e2, hdt2);
             hw_step2(t1, J1, fma2(ctP, nc, sb), e2, hdt2);
             hw_step2(t2, J2, fma2(ctM, nc, sb), e2, hdt2);
+            if (FD) {
+                const float4 m4 = dm4[pk], p4 = dp4[pk];
+                const float2 ma = make_float2(m4.x, m4.y), mb = make_float2(m4.z, m4.w);
+                const float2 pa = make_float2(p4.x, p4.y), pb = make_float2(p4.z, p4.w);
+                hw_step2(bm.r1, bm.I1, fma2(ns, smP, ma), e2, hdt2);
+                hw_step2(bm.r2, bm.I2, fma2(ns, smM, ma), e2, hdt2);
+                hw_step2(bp.r1, bp.I1, fma2(ns, spP, pa), e2, hdt2);
+                hw_step2(bp.r2, bp.I2, fma2(ns, spM, pa), e2, hdt2);
+                hw_step2(bm.r1, bm.I1, fma2(nc, smP, mb), e2, hdt2);
+                hw_step2(bm.r2, bm.I2, fma2(nc, smM, mb), e2, hdt2);
+                hw_step2(bp.r1, bp.I1, fma2(nc, spP, pb), e2, hdt2);
+                hw_step2(bp.r2, bp.I2, fma2(nc, spM, pb), e2, hdt2);
+            }
         };
         auto pair_plain = [&](int pk, float2 ns, float2 nc) {     // after S1: curve only
             const float4 d = drift4[pk];
@@ -252,6 +283,20 @@ fused_kernel(StreamGeom g, SeedArgs seeds, ModelDev md, ScenDev sc, const BondPl
                 const double w = warp_sum(ext[k]);
                 if (lane == 0) wext[warp][k] = w;
             }
+            if (FD) {
+#pragma unroll
+                for (int b = 0; b < 2; ++b) {
+                    float2 y1, y2, k1, k2;
+                    zbc_payoffs(b ? bp : bm, plans[1 + b], K, y1, y2, k1, k2);
+                    const float2 mom5[5] = {add2(y1, y2), add2(k1, k2), fma2(y1, y1, mul2(y2, y2)),
+                                            fma2(k1, k1, mul2(k2, k2)), fma2(k1, y1, mul2(k2, y2))};
+#pragma unroll
+                    for (int k = 0; k < 5; ++k) {
+                        const double w = warp_sum((double)mom5[k].x * mA + (double)mom5[k].y * mB);
+                        if (lane == 0) wext[warp][kFusedExtra + 5 * b + k] = w;
+                    }
+                }
+            }
         }
         for (int m = m_S1 + 1; m < n_mat; ++m) { advance_pairs(t, pair, half, pair_plain); save_curve(m); }
         __syncthreads();
@@ -261,7 +306,7 @@ fused_kernel(StreamGeom g, SeedArgs seeds, ModelDev md, ScenDev sc, const BondPl
             for (int w = 1; w < kWarps; ++w) acc += (double)wflt[w * 2 * n_mat + k];
             bacc[k] += acc;
         }
-        if (tid < kFusedExtra) {
+        if (tid < kExt) {
             double acc = wext[0][tid];
 #pragma unroll
             for (int w = 1; w < kWarps; ++w) acc += wext[w][tid];

@@ -274,6 +274,27 @@ class Engine:
                                                        n_steps_S1, _ptr(vega), C.byref(ms)))
         return vega, ms.value
 
+    # -- fused single-window pass: curve + ZBC/CV + pathwise vega + CRN FD bumps in ONE launch --
+    def fused(self, rng, P_mkt, f_mkt, eps=0.001, S1=5.0, S2=10.0, K=None, n_steps_S1=-1):
+        P_mkt, f_mkt = _f32(P_mkt, self.n_mat), _f32(f_mkt, self.n_mat)
+        P, f, se = (np.zeros(self.n_mat, np.float32) for _ in range(3))
+        z, v, ms = ZbcResult(), VegaResult(), C.c_float()
+        self._check(self._lib.hw1f_fused(self._h, rng._h, S1, S2, self.K_DEFAULT if K is None else K, _ptr(P_mkt),
+                                         _ptr(f_mkt), eps, n_steps_S1, _ptr(P), _ptr(f), _ptr(se), C.byref(z),
+                                         C.byref(v), C.byref(ms)))
+        return {"P": P, "f": f, "P_se": se, "zbc": z.as_dict(), "vega": v.as_dict(), "sim_ms": ms.value}
+
+    def fused_moments(self, rng, P_mkt, f_mkt, d_moments_ptr, eps=None, S1=5.0, S2=10.0, K=None, n_steps_S1=-1):
+        """async; eps=None: 2*n_mat+8 doubles, eps given: 2*n_mat+18 (FD bumps ride along)"""
+        P_mkt, f_mkt = _f32(P_mkt, self.n_mat), _f32(f_mkt, self.n_mat)
+        K = self.K_DEFAULT if K is None else K
+        if eps is None:
+            self._check(self._lib.hw1f_fused_moments(self._h, rng._h, S1, S2, K, _ptr(P_mkt), _ptr(f_mkt), n_steps_S1,
+                                                     C.c_void_p(d_moments_ptr)))
+        else:
+            self._check(self._lib.hw1f_fused_fd_moments(self._h, rng._h, S1, S2, K, _ptr(P_mkt), _ptr(f_mkt), eps,
+                                                        n_steps_S1, C.c_void_p(d_moments_ptr)))
+
     # -- simulate_paths_show (src/1:156-171) --
     def sample_paths(self, rng, n_show=32):
         out = np.zeros((n_show, self.n_steps + 1), np.float32)

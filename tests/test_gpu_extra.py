@@ -151,3 +151,22 @@ def test_drivers_match_reference_binaries(driver_runs):
     zr = np.loadtxt(ref / "data" / "zbc_bootstrap_optimal.csv", delimiter=",", skiprows=1)
     assert np.abs(zm[:, 1] / zr[:, 1] - 1).max() < 1e-4      # CV-adjusted prices
     assert np.abs(zm[:, 2] / zr[:, 2] - 1).max() < 1e-4      # raw prices
+
+
+def test_fused_with_fd_bumps_one_launch(engine, hw, curve):
+    """hw1f_fused: curve + ZBC/CV + antithetic pathwise vega + CRN FD bumps from ONE launch equal the
+    separate entry points evaluated on the same draw window"""
+    before = engine.launch_count
+    got = engine.fused(hw.Rng(SEED, N), curve["P"], curve["f"], eps=0.001, n_steps_S1=500)
+    sim_launches = engine.launch_count - before
+    assert sim_launches <= 8                              # plans x2, prep, ONE simulation kernel, reduce, un-centre, epilogue
+    sep_curve = engine.bond_curve(hw.Rng(SEED, N))
+    assert (got["P"] == sep_curve["P"]).all() and np.abs(got["f"] - sep_curve["f"]).max() == 0
+    z = engine.zbc_cv(hw.Rng(SEED, N), curve["P"], curve["f"], n_steps_S1=500)
+    assert got["zbc"]["price_cv"] == z["price_cv"] and got["zbc"]["beta"] == z["beta"]
+    fd = engine.vega_fd(hw.Rng(SEED, N), curve["P"], curve["f"], eps=0.001, n_steps_S1=500)   # same window [0,500)
+    assert got["vega"]["price_minus"] == fd["price_minus"] and got["vega"]["price_plus"] == fd["price_plus"]
+    assert got["vega"]["vega_fd"] == fd["vega_fd"]
+    pw = engine.vega_pathwise(hw.Rng(SEED, N), curve["P"], curve["f"], n_steps_S1=500)
+    assert abs(got["vega"]["vega_pathwise_f64"] - pw["vega_pathwise_f64"]) < 4 * pw["vega_pathwise_se"]
+    assert 0 < got["vega"]["vega_pathwise_se"] < pw["vega_pathwise_se"]      # antithetic twins: smaller error
