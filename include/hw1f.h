@@ -106,6 +106,9 @@ int hw1f_rng_tell(const hw1f_rng* rng, uint64_t* normal_offset);
 /* the state restore of src/3:422,434,502,509 */
 int hw1f_rng_seek(hw1f_rng* rng, uint64_t normal_offset);
 int hw1f_rng_info(const hw1f_rng* rng, uint64_t* seed, uint64_t* first_path, uint64_t* n_paths);
+/* optional: build and cache the seed-independent jump tables for this handle's path range on `eng`
+ * now (they are otherwise built by the first launch that needs them) */
+int hw1f_rng_prepare(hw1f_engine* eng, const hw1f_rng* rng);
 
 /* ---- Q1: zero-coupon curve -------------------------------------------------------- */
 /* simulate_zcb<<<NB,NTPB>>> + compute_average_and_forward<<<1,128>>>
@@ -219,6 +222,27 @@ int hw1f_fused(hw1f_engine* eng, hw1f_rng* rng, float S1, float S2, float K,
                const float* P_mkt, const float* f_mkt, float eps, int32_t n_steps_S1,
                float* P, float* f, float* P_se, hw1f_zbc_result* zbc, hw1f_vega_result* vega,
                float* sim_ms);
+
+/* ---- single-process multi-GPU front end ------------------------------------------------------ */
+/* One engine per device, paths sharded by contiguous XORWOW subsequence range (the union equals the
+ * single-GPU path set bit for bit), ONE ncclAllReduce(ncclDouble, ncclSum) of the packed moment vector
+ * per call, finalisation on device 0.  Nothing in the reference corresponds to this (it is single-GPU;
+ * select_gpu() merely picks one device, common.cuh:122-141).  n_gpus <= 0 uses every visible device.
+ * NCCL is dlopen'ed here; with one GPU no NCCL is needed. */
+typedef struct hw1f_multi hw1f_multi;
+int hw1f_multi_create(int n_gpus, hw1f_multi** out);
+int hw1f_multi_destroy(hw1f_multi* m);
+int hw1f_multi_device_count(const hw1f_multi* m, int* n_gpus);
+const char* hw1f_multi_last_error(const hw1f_multi* m);
+int hw1f_multi_set_model(hw1f_multi* m, const hw1f_params* p);
+int hw1f_multi_bond_curve(hw1f_multi* m, uint64_t seed, uint64_t n_paths_total, uint64_t normal_offset,
+                          float* P, float* f, float* P_se, float* wall_ms);
+int hw1f_multi_zbc_cv(hw1f_multi* m, uint64_t seed, uint64_t n_paths_total, uint64_t normal_offset,
+                      float S1, float S2, float K, const float* P_mkt, const float* f_mkt,
+                      int32_t n_steps_S1, hw1f_zbc_result* out);
+int hw1f_multi_vega_pathwise(hw1f_multi* m, uint64_t seed, uint64_t n_paths_total, uint64_t normal_offset,
+                             float S1, float S2, float K, const float* P_mkt, const float* f_mkt,
+                             int32_t n_steps_S1, double* vega, double* vega_se);
 
 /* ---- sample trajectories -------------------------------------------------------------- */
 /* simulate_paths_show<<<1,32>>> (market_data.cuh:136-160; src/1:163): r_paths[n_show*(n_steps+1)].

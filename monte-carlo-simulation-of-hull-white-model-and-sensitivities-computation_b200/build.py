@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libhw1f.so")
-SOURCES = ["hw1f_api.cu", "xorwow_jump.cpp"]
+SOURCES = ["hw1f_api.cu", "hw1f_multi.cu", "xorwow_jump.cpp"]
 HEADERS = ["hw1f_kernels.cuh", "hw1f_device.cuh", "hw1f_probe.cuh", "hw1f_kernels_extra.cuh", "xorwow_jump.hpp", os.path.join("..", "..", "include", "hw1f.h")]
 
 NVCC_FLAGS = [
@@ -23,6 +23,8 @@ NVCC_FLAGS = [
     # contraction is disabled so that nothing fuses behind our back.
     "-ftz=true", "-fmad=false",
     "-Xcompiler", "-fPIC", "-shared",
+    "-I/usr/include",          # nccl.h (types only; NCCL itself is dlopen'ed by hw1f_multi_create)
+    "-ldl",
 ]
 
 

@@ -54,6 +54,7 @@ struct Scenario {
 struct hw1f_engine {
     int device = -1;
     int sm_count = 148;
+    size_t smem_optin = 0;
     cudaStream_t stream = nullptr, own_stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_stage = nullptr;
     std::string err = "";
@@ -381,13 +382,24 @@ size_t smem_curve(const hw1f_engine* e, int nscen)
            (size_t)kWarps * nq * sizeof(float) + (size_t)nscen * e->p.n_mat * sizeof(float);
 }
 
+// dynamic shared memory: every simulation kernel is opted in to the device maximum ONCE at engine
+// creation (init_kernels); per launch only the requested size is checked
 template <class K>
-int set_smem(hw1f_engine* e, K kernel, size_t bytes)
+int set_smem(hw1f_engine* e, K, size_t bytes)
 {
-    HW_CUDA(e, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-    HW_CUDA(e, cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                    (int)cudaSharedmemCarveoutMaxShared));
+    if (bytes > e->smem_optin) {
+        e->err = "model too large for shared memory (n_steps * scenarios)";
+        return HW1F_ERR_UNSUPPORTED;
+    }
     return HW1F_OK;
+}
+
+template <class K>
+cudaError_t opt_in(K kernel, size_t bytes)
+{
+    cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (err != cudaSuccess) return err;
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
 }
 
 // ---- Q1 launch: sums for NSCEN scenarios into d_moments[n_runs][nscen*2*n_mat] -----------------
@@ -490,6 +502,35 @@ void zbc_algebra(const double mom[5], uint64_t n_paths_total, float P0S2, int32_
     r->ci95_hi = r->price_cv_f64 + 1.959963984540054 * r->se_cv;
 }
 
+// loads every simulation kernel and opts it in to the full shared-memory carve-out (once per engine)
+int init_kernels(hw1f_engine* e)
+{
+    const size_t b = e->smem_optin;
+    HW_CUDA(e, opt_in(bond_curve_kernel<1>, b));
+    HW_CUDA(e, opt_in(bond_curve_kernel<2>, b));
+    HW_CUDA(e, opt_in(zbc_kernel<1>, b));
+    HW_CUDA(e, opt_in(zbc_kernel<2>, b));
+    HW_CUDA(e, opt_in(pathwise_kernel, b));
+    HW_CUDA(e, opt_in(fused_kernel<false>, b));
+    HW_CUDA(e, opt_in(fused_kernel<true>, b));
+    HW_CUDA(e, opt_in(zbc_sum_kernel<0>, b));
+    HW_CUDA(e, opt_in(zbc_sum_kernel<1>, b));
+    HW_CUDA(e, opt_in(zbc_sum_kernel<2>, b));
+    HW_CUDA(e, opt_in(zbc_sum_kernel<3>, b));
+    return ensure_tables(e);
+}
+
+// seed-independent tables for a handle's path range (built once, cached): keeps one-off work out
+// of the event-timed region of the public calls
+int warm_geometry(hw1f_engine* e, const hw1f_rng* rng)
+{
+    HW_TRY(ensure_tables(e));
+    const uint32_t L_log2 = pick_L_log2(rng->n_paths);
+    const uint64_t last_path = rng->first_path + rng->n_paths - 1;
+    HW_REQUIRE(e, (last_path >> L_log2) < (1ull << 32), "path index too large for the jump tables (>= 2^41)");
+    return ensure_windows(e, L_log2, (uint32_t)(rng->first_path >> L_log2), (uint32_t)(last_path >> L_log2));
+}
+
 }  // namespace
 
 // =================================================================================================
@@ -545,6 +586,7 @@ int hw1f_engine_create(int device, hw1f_engine** out)
         return HW1F_ERR_UNSUPPORTED;
     }
     e->sm_count = prop.multiProcessorCount;
+    e->smem_optin = prop.sharedMemPerBlockOptin;
     if (cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreate(&e->ev0) != cudaSuccess || cudaEventCreate(&e->ev1) != cudaSuccess ||
         cudaEventCreateWithFlags(&e->ev_stage, cudaEventDisableTiming) != cudaSuccess) {
@@ -552,6 +594,11 @@ int hw1f_engine_create(int device, hw1f_engine** out)
         return HW1F_ERR_CUDA;
     }
     e->stream = e->own_stream;
+    if (init_kernels(e) != HW1F_OK) {
+        std::fprintf(stderr, "hw1f_engine_create: %s\n", e->err.c_str());
+        hw1f_engine_destroy(e);
+        return HW1F_ERR_CUDA;
+    }
     *out = e;
     return HW1F_OK;
 }
@@ -721,6 +768,13 @@ int hw1f_rng_info(const hw1f_rng* r, uint64_t* seed, uint64_t* first, uint64_t* 
     return HW1F_OK;
 }
 
+int hw1f_rng_prepare(hw1f_engine* e, const hw1f_rng* rng)
+{
+    if (!e || !rng) return HW1F_ERR_INVALID;
+    HW_CUDA(e, cudaSetDevice(e->device));
+    return warm_geometry(e, rng);
+}
+
 // ---- Q1 ----------------------------------------------------------------------------------------
 int hw1f_bond_curve_moments(hw1f_engine* e, hw1f_rng* rng, double* d_moments)
 {
@@ -769,6 +823,7 @@ int hw1f_bond_curve(hw1f_engine* e, hw1f_rng* rng, float* P, float* f, float* P_
     if (!rng) return HW1F_ERR_INVALID;
     HW_CUDA(e, cudaSetDevice(e->device));
     HW_CUDA(e, e->d_moments.ensure(4 * (size_t)e->p.n_mat * kMaxRuns));
+    HW_TRY(warm_geometry(e, rng));
     HW_CUDA(e, cudaEventRecord(e->ev0, e->stream));
     HW_TRY(hw1f_bond_curve_moments(e, rng, e->d_moments.p));
     HW_CUDA(e, cudaEventRecord(e->ev1, e->stream));
@@ -840,6 +895,7 @@ int hw1f_zbc_cv(hw1f_engine* e, hw1f_rng* rng, float S1, float S2, float K, cons
     int32_t n = 0;
     HW_TRY(resolve_steps(e, S1, n_steps_S1, &n));
     HW_CUDA(e, e->d_moments.ensure(4 * (size_t)e->p.n_mat * kMaxRuns));
+    HW_TRY(warm_geometry(e, rng));
     HW_CUDA(e, cudaEventRecord(e->ev0, e->stream));
     HW_TRY(hw1f_zbc_cv_moments(e, rng, S1, S2, K, P_mkt, f_mkt, n, e->d_moments.p));
     HW_CUDA(e, cudaEventRecord(e->ev1, e->stream));
@@ -864,6 +920,10 @@ int hw1f_zbc_cv_batch(hw1f_engine* e, const uint64_t* seeds, int32_t n_runs, uin
     HW_TRY(upload_market(e, 0, P_mkt, f_mkt));
     const ScenDev sc = scen_dev(e, e->p.sigma, e->sig_st, 0);
     HW_TRY(launch_plans(e, &sc, 1, S1, S2));
+    {
+        const hw1f_rng geom{0, 0, n_paths, 0};
+        HW_TRY(warm_geometry(e, &geom));
+    }
     HW_CUDA(e, cudaEventRecord(e->ev0, e->stream));
     for (int32_t done = 0; done < n_runs; done += kMaxRuns) {
         const int nb = (n_runs - done < kMaxRuns) ? (n_runs - done) : kMaxRuns;
@@ -908,6 +968,7 @@ int hw1f_vega_pathwise(hw1f_engine* e, hw1f_rng* rng, float S1, float S2, float 
     int32_t n = 0;
     HW_TRY(resolve_steps(e, S1, n_steps_S1, &n));
     HW_CUDA(e, e->d_moments.ensure(4 * (size_t)e->p.n_mat * kMaxRuns));
+    HW_TRY(warm_geometry(e, rng));
     HW_CUDA(e, cudaEventRecord(e->ev0, e->stream));
     HW_TRY(hw1f_vega_pathwise_moments(e, rng, S1, S2, K, P_mkt, f_mkt, n, e->d_moments.p));
     HW_CUDA(e, cudaEventRecord(e->ev1, e->stream));
@@ -936,6 +997,10 @@ int hw1f_vega_pathwise_batch(hw1f_engine* e, const uint64_t* seeds, int32_t n_ru
     HW_TRY(upload_market(e, 0, P_mkt, f_mkt));
     const ScenDev sc = scen_dev(e, e->p.sigma, e->sig_st, 0);
     HW_TRY(launch_plans(e, &sc, 1, S1, S2));
+    {
+        const hw1f_rng geom{0, 0, n_paths, 0};
+        HW_TRY(warm_geometry(e, &geom));
+    }
     HW_CUDA(e, cudaEventRecord(e->ev0, e->stream));
     for (int32_t done = 0; done < n_runs; done += kMaxRuns) {
         const int nb = (n_runs - done < kMaxRuns) ? (n_runs - done) : kMaxRuns;
@@ -981,6 +1046,7 @@ int hw1f_vega_fd(hw1f_engine* e, hw1f_rng* rng, float S1, float S2, float K, con
     HW_TRY(upload_market(e, 0, P_mkt, f_mkt));
     HW_TRY(upload_market(e, 1, P_mkt, f_mkt));
     ScenDev sc[2] = {scen_dev(e, sig_m, host_sig_st(e->p, sig_m), 2), scen_dev(e, sig_p, host_sig_st(e->p, sig_p), 3)};
+    HW_TRY(warm_geometry(e, rng));
     HW_CUDA(e, cudaEventRecord(e->ev0, e->stream));
     HW_TRY(launch_plans(e, sc, 2, S1, S2));
     Launch L;
@@ -1022,6 +1088,7 @@ int hw1f_vega_fd_recalibrated(hw1f_engine* e, hw1f_rng* rng, float S1, float S2,
     // normals [off, off+n) with the recalibrated curves, base drift, bumped sig_st and sigma.
     const float sig_m = e->p.sigma - eps, sig_p = e->p.sigma + eps;
     ScenDev sc[2] = {scen_dev(e, sig_m, host_sig_st(e->p, sig_m), 0), scen_dev(e, sig_p, host_sig_st(e->p, sig_p), 0)};
+    HW_TRY(warm_geometry(e, rng));
     HW_CUDA(e, cudaEventRecord(e->ev0, e->stream));
     Launch L;
     HW_TRY(prepare_launch(e, &rng->seed, 1, rng->first_path, rng->n_paths, rng->offset, &L));
@@ -1147,6 +1214,7 @@ int hw1f_fused(hw1f_engine* e, hw1f_rng* rng, float S1, float S2, float K, const
     HW_TRY(resolve_steps(e, S1, n_steps_S1, &n));
     const int nm = e->p.n_mat, next = kFusedExtra + kFusedFdExtra;
     HW_CUDA(e, e->d_moments.ensure(4 * (size_t)nm * kMaxRuns));
+    HW_TRY(warm_geometry(e, rng));
     HW_CUDA(e, cudaEventRecord(e->ev0, e->stream));
     HW_TRY(fused_launch(e, rng, S1, S2, K, P_mkt, f_mkt, true, eps, n, e->d_moments.p));
     HW_CUDA(e, cudaEventRecord(e->ev1, e->stream));

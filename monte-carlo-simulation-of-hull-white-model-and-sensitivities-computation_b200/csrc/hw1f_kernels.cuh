@@ -185,7 +185,7 @@ build_hi_kernel(uint32_t hi_base, uint32_t L_log2, const uint32_t* __restrict__ 
 struct ThreadStreams {
     Xorwow A, B;
     bool validA, validB;
-    uint32_t dcur;
+    uint32_t dcur, dcurB;
 };
 
 __device__ __forceinline__ ThreadStreams derive_streams(const StreamGeom& g, const SeedArgs& seeds, int run,
@@ -217,9 +217,11 @@ __device__ __forceinline__ ThreadStreams derive_streams(const StreamGeom& g, con
     t.validB = (pB >= g.first_path) && (pB < g.first_path + g.n_paths);
     // keep the Weyl word in a vector register: xorshift + Weyl + immediate is then ONE IADD3 per
     // draw instead of a uniform-datapath add plus a vector add
-    // (bit 63 of a path index is always 0; the dependence on pA only defeats uniform-register
-    // allocation of this loop-carried value)
+    // (bit 63 of a path index is always 0; the dependence on pA / pB only defeats uniform-register
+    // allocation and common-subexpression merging: with one private Weyl register per stream,
+    // xorshift + Weyl + immediate is a single IADD3 per draw)
     t.dcur = seeds.s[run].d_start + (uint32_t)(pA >> 63);
+    t.dcurB = seeds.s[run].d_start + (uint32_t)(pB >> 63);
     return t;
 }
 
@@ -231,14 +233,15 @@ __device__ __forceinline__ void run_pairs(ThreadStreams& t, int pair, PairFn&& f
 #pragma unroll
     for (int j = 0; j < NP; ++j) {
         const uint32_t xa = t.A.next() + (t.dcur + kWeyl * (2 * j + 1));
-        const uint32_t xb = t.B.next() + (t.dcur + kWeyl * (2 * j + 1));
+        const uint32_t xb = t.B.next() + (t.dcurB + kWeyl * (2 * j + 1));
         const uint32_t ya = t.A.next() + (t.dcur + kWeyl * (2 * j + 2));
-        const uint32_t yb = t.B.next() + (t.dcur + kWeyl * (2 * j + 2));
+        const uint32_t yb = t.B.next() + (t.dcurB + kWeyl * (2 * j + 2));
         float2 ns, nc;
         box_muller2(xa, ya, xb, yb, ns, nc);
         f(pair + j, ns, nc);
     }
     t.dcur += kWeyl * (2 * NP);
+    t.dcurB += kWeyl * (2 * NP);
 }
 
 // advance `n_pairs` Box-Muller pairs starting at pair index `pair` (unrolled by 5 pairs = 10 draws,
@@ -254,9 +257,10 @@ __device__ __forceinline__ void advance_pairs(ThreadStreams& t, int& pair, int n
 // one isolated pair (lead / tail handling of odd normal offsets and odd step counts)
 __device__ __forceinline__ void one_pair(ThreadStreams& t, float2& ns, float2& nc)
 {
-    const uint32_t xa = t.A.next() + (t.dcur + kWeyl), xb = t.B.next() + (t.dcur + kWeyl);
-    const uint32_t ya = t.A.next() + (t.dcur + 2 * kWeyl), yb = t.B.next() + (t.dcur + 2 * kWeyl);
+    const uint32_t xa = t.A.next() + (t.dcur + kWeyl), xb = t.B.next() + (t.dcurB + kWeyl);
+    const uint32_t ya = t.A.next() + (t.dcur + 2 * kWeyl), yb = t.B.next() + (t.dcurB + 2 * kWeyl);
     t.dcur += 2 * kWeyl;
+    t.dcurB += 2 * kWeyl;
     box_muller2(xa, ya, xb, yb, ns, nc);
 }
 

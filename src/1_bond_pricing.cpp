@@ -23,7 +23,27 @@ int main()
     std::vector<float> P(nm), f(nm), se(nm);
     float sim_ms = 0.f;
     std::printf("Running Monte Carlo simulation...\n");
-    require(hw1f_bond_curve(eng.h, rng.h, P.data(), f.data(), se.data(), &sim_ms), eng.h, "hw1f_bond_curve");
+    int gpus = 1;
+    if (const char* s = std::getenv("HW_GPUS")) gpus = std::atoi(s);
+    if (gpus > 1) {
+        // same path set, sharded by subsequence range over `gpus` devices + one NCCL all-reduce
+        hw1f_multi* m = nullptr;
+        if (hw1f_multi_create(gpus, &m) != HW1F_OK) { std::fprintf(stderr, "hw1f_multi_create failed\n"); return 1; }
+        uint64_t seed = 0;
+        hw1f_rng_info(rng.h, &seed, nullptr, nullptr);
+        if (hw1f_multi_set_model(m, &p) != HW1F_OK ||
+            hw1f_multi_bond_curve(m, seed, kNPaths, 0, P.data(), f.data(), se.data(), &sim_ms) != HW1F_OK) {
+            std::fprintf(stderr, "multi-GPU run failed: %s\n", hw1f_multi_last_error(m));
+            return 1;
+        }
+        int used = 0;
+        hw1f_multi_device_count(m, &used);
+        std::printf("(sharded over %d GPUs)\n", used);
+        hw1f_multi_destroy(m);
+        hw1f_rng_seek(rng.h, (uint64_t)p.n_steps);   // where the single-GPU run would have left the streams
+    } else {
+        require(hw1f_bond_curve(eng.h, rng.h, P.data(), f.data(), se.data(), &sim_ms), eng.h, "hw1f_bond_curve");
+    }
     std::printf("Simulation complete\n\nRESULTS\nT (years)    P(0,T)         f(0,T)\n");
     for (int i = 0; i < nm; i += stride)
         std::printf("%5.1f        %.6f       %7.4f%%\n", i * eng.c.mat_spacing, P[i], f[i] * 100.0f);
