@@ -275,7 +275,10 @@ def main():
     achieved = per_gpu * ALGO_ISSUE_PER_PATHSTEP
     roofline = {
         "bound": "issue", "achieved": achieved / 1e9, "peak": issue_peak / 1e9, "unit": "Ginstr/s (thread-level)",
-        "frac": achieved / issue_peak, "traffic": None,
+        "frac": achieved / issue_peak,
+        # dram__bytes_read.sum + dram__bytes_write.sum of one bond_curve_kernel launch
+        # (profiles/r01_ncu_full_bond_curve_v3.csv): window tables, L2-resident after first touch
+        "traffic": 6635008, "traffic_unit": "bytes per launch (ncu --set full)",
         "peak_source": "measured by hw1f_pipe_probe on this GPU in this run (FFMA / LOP3 / mixed streams); "
                        "MEASURED_PEAKS.json has no FP32/XU entry (HBM and bf16 tensor only)",
         "issue_peak_nominal_at_clock": issue_peak_nominal / 1e9,
@@ -295,14 +298,21 @@ def main():
     if world == 1 and not args.no_cpu_baseline:
         from oracle_lib import Oracle
         o = Oracle()
-        n_cpu = 1 << 16                                # BASELINE.json configs[0]: oracle at 2^16 paths
-        o.bond_curve(1, 1 << 10)
+        # bounded sample of the same workload sized for ~10 s of wall time on this box's cores
+        # (BASELINE.json configs[0] runs the oracle at 2^16; more cores -> a bigger sample)
+        t0 = time.time()
+        o.bond_curve(1, 1 << 14)
+        t_cal = max(time.time() - t0, 1e-3)
+        lg = 14
+        while lg < 22 and t_cal * (1 << (lg + 1 - 14)) < 12.0:
+            lg += 1
+        n_cpu = 1 << max(lg, 16)
         t0 = time.time()
         o.bond_curve(1234, n_cpu)
         dt = time.time() - t0
         cpu_baseline = {"value": 2.0 * n_cpu * n_steps / dt, "unit": UNIT, "cores": o.max_threads(), "kind": "port",
-                        "sample": f"OpenMP C oracle (oracle/hw1f_oracle.c), Q1 at 2^16 subsequences x 2 x 1000 steps, "
-                                  f"{dt:.2f} s wall"}
+                        "sample": f"OpenMP C oracle (oracle/hw1f_oracle.c), Q1 at 2^{n_cpu.bit_length() - 1} "
+                                  f"subsequences x 2 x 1000 steps, {dt:.2f} s wall"}
 
     bad = {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"} & set(clocks.get("reasons", []))
     line = {
@@ -316,7 +326,7 @@ def main():
                    "outside the per-step event pairs)", "parallelism": f"path-range sharding x{world}, one NCCL "
                    "all-reduce of 202 doubles per step" if world > 1 else "single GPU"},
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms,
-                "h2d_bytes_per_step": 2 * (n_steps + 2) * 8, "d2h_bytes_per_step": 3 * n_mat * 4},
+                "h2d_bytes_per_step": 2 * (n_steps + 2) * 8 + n_mat * 4, "d2h_bytes_per_step": 3 * n_mat * 4},
         "gpu_launches": int(launches),
         "clocks": clocks, "clock_check": "rejected: thermal/hw slowdown seen" if bad else "ok",
         "roofline": roofline,

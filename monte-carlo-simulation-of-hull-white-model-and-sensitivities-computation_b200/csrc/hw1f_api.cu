@@ -387,7 +387,7 @@ size_t smem_curve(const hw1f_engine* e, int nscen)
 template <class K>
 int set_smem(hw1f_engine* e, K, size_t bytes)
 {
-    if (bytes > e->smem_optin) {
+    if (bytes + 2048 > e->smem_optin) {   // 2 KB head-room for the kernels' static shared arrays
         e->err = "model too large for shared memory (n_steps * scenarios)";
         return HW1F_ERR_UNSUPPORTED;
     }
@@ -397,7 +397,11 @@ int set_smem(hw1f_engine* e, K, size_t bytes)
 template <class K>
 cudaError_t opt_in(K kernel, size_t bytes)
 {
-    cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    cudaFuncAttributes attr;
+    cudaError_t err = cudaFuncGetAttributes(&attr, kernel);   // also forces the module load
+    if (err != cudaSuccess) return err;
+    if (bytes > attr.sharedSizeBytes) bytes -= attr.sharedSizeBytes;   // static + dynamic <= opt-in limit
+    err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (err != cudaSuccess) return err;
     return cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
 }
@@ -517,6 +521,19 @@ int init_kernels(hw1f_engine* e)
     HW_CUDA(e, opt_in(zbc_sum_kernel<1>, b));
     HW_CUDA(e, opt_in(zbc_sum_kernel<2>, b));
     HW_CUDA(e, opt_in(zbc_sum_kernel<3>, b));
+    // the small kernels have no dynamic shared memory; querying them loads their code now instead
+    // of inside the first timed call
+    cudaFuncAttributes attr;
+    HW_CUDA(e, cudaFuncGetAttributes(&attr, prep_lo_kernel));
+    HW_CUDA(e, cudaFuncGetAttributes(&attr, build_hi_kernel));
+    HW_CUDA(e, cudaFuncGetAttributes(&attr, bond_plan_kernel));
+    HW_CUDA(e, cudaFuncGetAttributes(&attr, reduce_partials_kernel<double>));
+    HW_CUDA(e, cudaFuncGetAttributes(&attr, reduce_curve_kernel));
+    HW_CUDA(e, cudaFuncGetAttributes(&attr, curve_epilogue_kernel));
+    HW_CUDA(e, cudaFuncGetAttributes(&attr, theta_kernel));
+    HW_CUDA(e, cudaFuncGetAttributes(&attr, fused_uncenter_kernel));
+    HW_CUDA(e, cudaFuncGetAttributes(&attr, sample_paths_kernel));
+    HW_CUDA(e, cudaFuncGetAttributes(&attr, steps_probe_kernel));
     return ensure_tables(e);
 }
 
@@ -528,7 +545,14 @@ int warm_geometry(hw1f_engine* e, const hw1f_rng* rng)
     const uint32_t L_log2 = pick_L_log2(rng->n_paths);
     const uint64_t last_path = rng->first_path + rng->n_paths - 1;
     HW_REQUIRE(e, (last_path >> L_log2) < (1ull << 32), "path index too large for the jump tables (>= 2^41)");
-    return ensure_windows(e, L_log2, (uint32_t)(rng->first_path >> L_log2), (uint32_t)(last_path >> L_log2));
+    HW_TRY(ensure_windows(e, L_log2, (uint32_t)(rng->first_path >> L_log2), (uint32_t)(last_path >> L_log2)));
+    // scratch every single-seed launch over this range will need (cudaMalloc is not free either)
+    HW_CUDA(e, e->d_U.ensure((size_t)5 << L_log2));
+    const unsigned long long n_chunks = (last_path >> kChunkLog2) - (rng->first_path >> kChunkLog2) + 1;
+    const unsigned long long cap = (unsigned long long)e->sm_count * 32ull;
+    const size_t grid = (size_t)(n_chunks < cap ? n_chunks : cap);
+    if (e->has_model) HW_CUDA(e, e->d_partials.ensure(grid * (4 * (size_t)e->p.n_mat + 32)));
+    return HW1F_OK;
 }
 
 }  // namespace
