@@ -35,9 +35,14 @@ for _p in (ROOT, os.path.join(ROOT, "tests")):
 METRIC = "HW1F path-steps/s (2M antithetic paths, 1000 steps)"
 UNIT = "path-steps/s"
 N_PATHS_LOG2 = 20          # reference N_PATHS = 1024*1024 (include/common.cuh:16)
-ALGO_ISSUE_PER_PATHSTEP = 12.0   # 6.75 FP32 + 1.0 MUFU + 3.75 INT + 0.5 I2F
-ALGO_FP32_PER_PATHSTEP = 6.75
-ALGO_XU_PER_PATHSTEP = 1.0
+# Algorithmic pipe instructions per path-step.
+#   reference-order arithmetic: 6.75 FP32 + 1.0 MUFU + 3.75 INT + 0.5 I2F = 12 issue slots
+#   decomposed arithmetic (default mode)   : 2.5 FP32 + 1.0 MUFU + 3.75 INT + 0.5 I2F = 7.75 issue slots
+#   Q1 adds 4 MUFU.EX2 per 40 path-steps at the save points: 1.1 MUFU per path-step in both modes
+ALGO = {
+    "decomposed": {"issue": 7.75, "fp32": 2.5, "xu": 1.1},
+    "reference_order": {"issue": 12.0, "fp32": 6.75, "xu": 1.1},
+}
 
 
 class ClockSampler(threading.Thread):
@@ -156,6 +161,8 @@ def main():
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--paths-log2", type=int, default=N_PATHS_LOG2, help="subsequences per GPU (default 2^20)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mode", default="decomposed", choices=["decomposed", "reference_order"],
+                    help="simulation arithmetic (include/hw1f.h HW1F_MODE_*); both give the same Gaussians")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -190,6 +197,7 @@ def main():
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
     eng = hw.Engine(device=local_rank, stream=stream.cuda_stream)
+    eng.set_mode(hw._ffi.MODE_DECOMPOSED if args.mode == "decomposed" else hw._ffi.MODE_REFERENCE_ORDER)
     n_paths = 1 << args.paths_log2
     n_steps, n_mat = eng.n_steps, eng.n_mat
     first_path = rank * n_paths                       # disjoint XORWOW subsequence ranges per rank
@@ -272,26 +280,52 @@ def main():
     issue_peak_nominal = sm_count * 4 * 32 * sm_mhz * 1e6        # lane-instructions/s at the clock seen
     issue_peak = max(ffma, alu, mix)                              # measured: best single-issue stream
     per_gpu = value / world
-    achieved = per_gpu * ALGO_ISSUE_PER_PATHSTEP
+    algo = ALGO[args.mode]
+    xu_frac = per_gpu * algo["xu"] / mufu
+    issue_frac = per_gpu * algo["issue"] / issue_peak
+    bound = "xu" if xu_frac >= issue_frac else "issue"
+    # the same steps in the other arithmetic mode, for transparency (device-timed)
+    other = "reference_order" if args.mode == "decomposed" else "decomposed"
+    eng.set_mode(hw._ffi.MODE_REFERENCE_ORDER if other == "reference_order" else hw._ffi.MODE_DECOMPOSED)
+    for i in range(3):
+        device_step(1000 + i)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n_other = min(args.steps, 50)
+    e0.record()
+    for i in range(n_other):
+        device_step(5000 + i)
+    e1.record()
+    torch.cuda.synchronize()
+    other_ms = e0.elapsed_time(e1) / n_other
+    eng.set_mode(hw._ffi.MODE_DECOMPOSED if args.mode == "decomposed" else hw._ffi.MODE_REFERENCE_ORDER)
     roofline = {
-        "bound": "issue", "achieved": achieved / 1e9, "peak": issue_peak / 1e9, "unit": "Ginstr/s (thread-level)",
-        "frac": achieved / issue_peak,
-        # dram__bytes_read.sum + dram__bytes_write.sum of one bond_curve_kernel launch
-        # (profiles/r01_ncu_full_bond_curve_v3.csv): window tables, L2-resident after first touch
+        # this path is bound by the SFU (XU) pipe and by instruction issue, not by HBM or tensor cores
+        # (SURVEY 8d); "achieved"/"peak" are for the binding resource, the other one is given beside it
+        "bound": bound,
+        "achieved": (per_gpu * algo["xu"] if bound == "xu" else per_gpu * algo["issue"]) / 1e9,
+        "peak": (mufu if bound == "xu" else issue_peak) / 1e9,
+        "unit": "G MUFU/s (thread-level)" if bound == "xu" else "Ginstr/s (thread-level)",
+        "frac": max(xu_frac, issue_frac),
+        # dram__bytes_read.sum + dram__bytes_write.sum of one simulation-kernel launch
+        # (profiles/r01_ncu_full_*.csv): window tables, L2-resident after first touch
         "traffic": 6635008, "traffic_unit": "bytes per launch (ncu --set full)",
-        "peak_source": "measured by hw1f_pipe_probe on this GPU in this run (FFMA / LOP3 / mixed streams); "
+        "peak_source": "measured by hw1f_pipe_probe on this GPU in this run (MUFU.EX2 / FFMA / LOP3 / mixed streams); "
                        "MEASURED_PEAKS.json has no FP32/XU entry (HBM and bf16 tensor only)",
-        "issue_peak_nominal_at_clock": issue_peak_nominal / 1e9,
-        "fp32_pipe": {"achieved": per_gpu * ALGO_FP32_PER_PATHSTEP / 1e9, "peak_ffma": ffma / 1e9,
-                      "peak_ffma2_lanes": 2 * ffma2 / 1e9,
-                      "frac": per_gpu * ALGO_FP32_PER_PATHSTEP / max(ffma, 2 * ffma2)},
-        "xu_pipe": {"achieved": per_gpu * ALGO_XU_PER_PATHSTEP / 1e9, "peak_mufu": mufu / 1e9,
-                    "frac": per_gpu * ALGO_XU_PER_PATHSTEP / mufu},
+        "mode": args.mode,
+        "xu_pipe": {"achieved": per_gpu * algo["xu"] / 1e9, "peak_mufu": mufu / 1e9, "frac": xu_frac},
+        "issue": {"achieved": per_gpu * algo["issue"] / 1e9, "peak_measured": issue_peak / 1e9,
+                  "peak_nominal_at_clock": issue_peak_nominal / 1e9, "frac": issue_frac},
+        "fp32_pipe": {"achieved": per_gpu * algo["fp32"] / 1e9, "peak_ffma": ffma / 1e9,
+                      "peak_ffma2_lanes": 2 * ffma2 / 1e9, "frac": per_gpu * algo["fp32"] / max(ffma, 2 * ffma2)},
         "probes_Ginstr_s": {"ffma": ffma / 1e9, "ffma2": ffma2 / 1e9, "mufu_ex2": mufu / 1e9, "lop3_shf": alu / 1e9,
                             "i2fp": i2f / 1e9, "hw1f_mix": mix / 1e9},
-        "algorithmic_per_path_step": {"issue": ALGO_ISSUE_PER_PATHSTEP, "fp32": ALGO_FP32_PER_PATHSTEP,
-                                      "xu": ALGO_XU_PER_PATHSTEP},
-        "kernel": "bond_curve_kernel<true,1> (prep_lo_kernel + reduce_partials_kernel included in the time)",
+        "algorithmic_per_path_step": algo,
+        "kernel": ("fast_kernel<1,0,0>" if args.mode == "decomposed" else "bond_curve_kernel<1>") +
+                  " (prep_lo_kernel + reduce_curve_kernel included in the time)",
+        "other_mode": {"mode": other, "ms_per_step": other_ms,
+                       "value": path_steps_per_step / world / (other_ms * 1e-3),
+                       "issue_frac": path_steps_per_step / world / (other_ms * 1e-3) * ALGO[other]["issue"] / issue_peak},
     }
 
     cpu_baseline = None
@@ -321,7 +355,7 @@ def main():
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"Q1 bond curve P(0,T), f(0,T): 2^{args.paths_log2} XORWOW subsequences x 2 antithetic "
                                f"paths x {n_steps} steps per GPU, r0=0.012 a=1 sigma=0.1, {n_mat} maturities, "
-                               "seeding included",
+                               "seeding included", "arithmetic": args.mode,
                    "paths_per_gpu": 2 * n_paths, "n_steps": n_steps, "l2": "flushed between steps (256 MiB memset, "
                    "outside the per-step event pairs)", "parallelism": f"path-range sharding x{world}, one NCCL "
                    "all-reduce of 202 doubles per step" if world > 1 else "single GPU"},

@@ -72,6 +72,17 @@ int hw1f_engine_destroy(hw1f_engine* eng);
 /* run on a caller-owned cudaStream_t (NULL = the engine's own stream) */
 int hw1f_engine_set_stream(hw1f_engine* eng, void* cuda_stream);
 int hw1f_engine_device(const hw1f_engine* eng, int* device);
+/* Simulation arithmetic.  Both modes consume bit-identical XORWOW integers and Box-Muller normals.
+ *   HW1F_MODE_REFERENCE_ORDER: every path is stepped with the reference's own float sequence
+ *       (FFMA, FFMA, FADD, FMUL, FFMA per path-step; include/common.cuh:237-244).
+ *   HW1F_MODE_DECOMPOSED (default): the model is linear in the shocks, so the +G/-G twins, the
+ *       sigma-bumped twins and the pathwise tangent are all (noise-free part) +/- scale * h with ONE
+ *       shared noise recursion h' = h e^{-a dt} + G per stream; per-path values differ from the
+ *       reference by float rounding only (~1e-7 relative; north-star tolerance 1e-5). */
+#define HW1F_MODE_REFERENCE_ORDER 0
+#define HW1F_MODE_DECOMPOSED 1
+int hw1f_engine_set_mode(hw1f_engine* eng, int mode);
+int hw1f_engine_get_mode(const hw1f_engine* eng, int* mode);
 int hw1f_engine_synchronize(hw1f_engine* eng);
 
 /* H_* constants of common.cuh:33-39 */

@@ -8,6 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("HW1F_LIB") or os.path.join(HERE, "lib", "libhw1f.so")
 
 OK = 0
+MODE_REFERENCE_ORDER, MODE_DECOMPOSED = 0, 1
 ERR_INVALID, ERR_CUDA, ERR_NO_DEVICE, ERR_UNSUPPORTED, ERR_NO_MODEL = 1, 2, 3, 4, 5
 
 
@@ -65,6 +66,8 @@ SYMBOLS = {
     "hw1f_engine_destroy": (C.c_int, [_P]),
     "hw1f_engine_set_stream": (C.c_int, [_P, _P]),
     "hw1f_engine_device": (C.c_int, [_P, C.POINTER(C.c_int)]),
+    "hw1f_engine_set_mode": (C.c_int, [_P, C.c_int]),
+    "hw1f_engine_get_mode": (C.c_int, [_P, C.POINTER(C.c_int)]),
     "hw1f_engine_synchronize": (C.c_int, [_P]),
     "hw1f_default_params": (C.c_int, [C.POINTER(Params)]),
     "hw1f_set_model": (C.c_int, [_P, C.POINTER(Params)]),

@@ -15,6 +15,7 @@
 
 #include "hw1f_kernels.cuh"
 #include "hw1f_kernels_extra.cuh"
+#include "hw1f_kernels_fast.cuh"
 #include "hw1f_probe.cuh"
 #include "xorwow_jump.hpp"
 
@@ -60,6 +61,7 @@ struct hw1f_engine {
     std::string err = "";
     uint64_t launches = 0;
 
+    int mode = HW1F_MODE_DECOMPOSED;
     bool has_model = false;
     hw1f_params p{};
     float dt = 0, spacing = 0, exp_adt = 0, sig_st = 0;
@@ -74,6 +76,10 @@ struct hw1f_engine {
     DevBuf<float2> d_drift[4];
     DevBuf<float> d_mkt;                 // [4][n_mat]: P0,f0,P1,f1
     DevBuf<float> d_center;              // [n_mat] centring constants of the curve accumulation
+    // noise-free ("deterministic") parts per drift slot, host double: det_m[slot][i] = short rate
+    // after i steps with G = 0, det_I[slot][i] its trapezoid integral (slot 1: tangent D, ID)
+    std::vector<double> det_m[4], det_I[4];
+    DevBuf<float> d_emI[4];              // [n_mat] exp(-det_I) at the save points (decomposed curve kernels)
     DevBuf<BondPlan> d_plans;
     DevBuf<double> d_partials;
     DevBuf<double> d_moments;            // internal moment vector
@@ -198,12 +204,29 @@ int download(hw1f_engine* e, void* dst, const void* src, size_t bytes)
 
 int upload_drift(hw1f_engine* e, int slot, const float* table)
 {
-    const int n = e->p.n_steps;
+    const int n = e->p.n_steps, nm = e->p.n_mat;
     HW_CUDA(e, e->d_drift[slot].ensure(n + 2));
     std::vector<float2> dup(n + 2);
     for (int i = 0; i < n; ++i) dup[i] = make_float2(table[i], table[i]);
     dup[n] = dup[n + 1] = make_float2(0.f, 0.f);
-    return upload(e, e->d_drift[slot].p, dup.data(), dup.size() * sizeof(float2));
+    HW_TRY(upload(e, e->d_drift[slot].p, dup.data(), dup.size() * sizeof(float2)));
+    // noise-free recursion with this table (start r0 for rate tables, 0 for the tangent table)
+    std::vector<double>& m = e->det_m[slot];
+    std::vector<double>& I = e->det_I[slot];
+    m.assign(n + 1, 0.0);
+    I.assign(n + 1, 0.0);
+    m[0] = (slot == 1) ? 0.0 : (double)e->p.r0;
+    for (int i = 0; i < n; ++i) {
+        m[i + 1] = m[i] * (double)e->exp_adt + (double)table[i];
+        I[i + 1] = I[i] + 0.5 * (m[i] + m[i + 1]) * (double)e->dt;
+    }
+    if (slot != 1) {
+        std::vector<float> emI(nm, 1.0f);
+        for (int k = 1; k < nm; ++k) emI[k] = (float)exp(-I[(size_t)k * e->stride]);
+        HW_CUDA(e, e->d_emI[slot].ensure(nm));
+        HW_TRY(upload(e, e->d_emI[slot].p, emI.data(), emI.size() * sizeof(float)));
+    }
+    return HW1F_OK;
 }
 
 ModelDev model_dev(const hw1f_engine* e)
@@ -319,10 +342,19 @@ int prepare_launch(hw1f_engine* e, const uint64_t* seeds, int n_runs, uint64_t f
     return HW1F_OK;
 }
 
+// sums `count` entries starting at `offset` of partials[run][block][stride] into d_out[run*out_stride + ..]
+int reduce_range(hw1f_engine* e, int n_runs, unsigned n_blocks, int stride, int offset, int count, double* d_out,
+                 int out_stride)
+{
+    if (count <= 0) return HW1F_OK;
+    reduce_partials_kernel<double><<<dim3(count, n_runs), 256, 0, e->stream>>>(e->d_partials.p + offset, (int)n_blocks,
+                                                                             stride, d_out, out_stride);
+    return check_launch(e, "reduce_partials_kernel");
+}
+
 int reduce_to(hw1f_engine* e, int n_runs, unsigned n_blocks, int nq, double* d_out)
 {
-    reduce_partials_kernel<double><<<dim3(nq, n_runs), 256, 0, e->stream>>>(e->d_partials.p, (int)n_blocks, nq, d_out);
-    return check_launch(e, "reduce_partials_kernel");
+    return reduce_range(e, n_runs, n_blocks, nq, 0, nq, d_out, nq);
 }
 
 int require_model(hw1f_engine* e)
@@ -375,6 +407,40 @@ ScenDev scen_dev(const hw1f_engine* e, float sigma, float sig_st, int drift_slot
     return s;
 }
 
+// decomposed-mode constants of one sigma scenario (drift slot selects the noise-free tables)
+FastScen fast_scen(const hw1f_engine* e, float sig_st, int drift_slot, int n_steps_S1)
+{
+    FastScen f;
+    f.sg = sig_st;
+    f.c = (0.5f * e->dt) * sig_st;
+    f.mS1 = (float)e->det_m[drift_slot][n_steps_S1];
+    f.ImS1 = (float)e->det_I[drift_slot][n_steps_S1];
+    f.emI = e->d_emI[drift_slot].p;
+    return f;
+}
+
+FastTangent fast_tangent(const hw1f_engine* e, int n_steps_S1)
+{
+    FastTangent t;
+    t.DS1 = (float)e->det_m[1][n_steps_S1];
+    t.IDS1 = (float)e->det_I[1][n_steps_S1];
+    return t;
+}
+
+int drift_slot_of(const hw1f_engine* e, const ScenDev& sc)
+{
+    for (int k = 0; k < 4; ++k)
+        if (sc.drift2 == e->d_drift[k].p) return k;
+    return 0;
+}
+
+size_t smem_fast(const hw1f_engine* e, int ncur)
+{
+    const size_t nqc = (size_t)ncur * 2 * e->p.n_mat;
+    return (size_t)kWinWords * 4 + nqc * sizeof(double) + (size_t)kWarps * nqc * sizeof(float) +
+           (size_t)ncur * e->p.n_mat * sizeof(float) + 64;
+}
+
 size_t smem_curve(const hw1f_engine* e, int nscen)
 {
     const int nq = nscen * 2 * e->p.n_mat;
@@ -409,10 +475,29 @@ cudaError_t opt_in(K kernel, size_t bytes)
 // ---- Q1 launch: sums for NSCEN scenarios into d_moments[n_runs][nscen*2*n_mat] -----------------
 int launch_curve(hw1f_engine* e, const Launch& L, const ScenDev* sc, int nscen, double* d_moments)
 {
-    const int nq = nscen * 2 * e->p.n_mat;
+    const int nm = e->p.n_mat, nq = nscen * 2 * nm;
     HW_CUDA(e, e->d_partials.ensure((size_t)L.n_runs * L.grid_x * nq));
-    const size_t smem = smem_curve(e, nscen);
     const dim3 grid(L.grid_x, L.n_runs);
+    if (e->mode == HW1F_MODE_DECOMPOSED) {
+        const int slot0 = drift_slot_of(e, sc[0]), slot1 = drift_slot_of(e, sc[nscen > 1 ? 1 : 0]);
+        const FastScen c0 = fast_scen(e, sc[0].sig_st, slot0, 0), c1 = fast_scen(e, sc[nscen > 1 ? 1 : 0].sig_st, slot1, 0);
+        const FastTangent tg{0.f, 0.f};
+        const size_t smem = smem_fast(e, nscen);
+        if (nscen == 1) {
+            HW_TRY(set_smem(e, fast_kernel<1, 0, 0>, smem));
+            fast_kernel<1, 0, 0><<<grid, kThreads, smem, e->stream>>>(L.g, L.seeds, model_dev(e), c0, c1, c0, c0, c0, tg,
+                                                                     e->d_plans.p, 0, 0, 0.f, e->d_partials.p);
+        } else {
+            HW_TRY(set_smem(e, fast_kernel<2, 0, 0>, smem));
+            fast_kernel<2, 0, 0><<<grid, kThreads, smem, e->stream>>>(L.g, L.seeds, model_dev(e), c0, c1, c0, c0, c0, tg,
+                                                                     e->d_plans.p, 0, 0, 0.f, e->d_partials.p);
+        }
+        HW_TRY(check_launch(e, "fast_kernel<curve>"));
+        reduce_curve_kernel<<<dim3(nm, L.n_runs * nscen), 256, 0, e->stream>>>(
+            e->d_partials.p, (int)L.grid_x, nq, nscen, nm, c0.emI, c1.emI, 2.0f, L.g.n_paths, d_moments, nq);
+        return check_launch(e, "reduce_curve_kernel");
+    }
+    const size_t smem = smem_curve(e, nscen);
     if (nscen == 1) {
         HW_TRY(set_smem(e, bond_curve_kernel<1>, smem));
         bond_curve_kernel<1><<<grid, kThreads, smem, e->stream>>>(L.g, L.seeds, model_dev(e), sc[0], sc[0],
@@ -423,9 +508,9 @@ int launch_curve(hw1f_engine* e, const Launch& L, const ScenDev* sc, int nscen, 
                                                                   e->d_partials.p);
     }
     HW_TRY(check_launch(e, "bond_curve_kernel"));
-    reduce_curve_kernel<<<dim3(e->p.n_mat, L.n_runs * nscen), 256, 0, e->stream>>>(
-        e->d_partials.p, (int)L.grid_x, nscen, e->p.n_mat, sc[0].center, sc[nscen > 1 ? 1 : 0].center, L.g.n_paths,
-        d_moments);
+    reduce_curve_kernel<<<dim3(nm, L.n_runs * nscen), 256, 0, e->stream>>>(
+        e->d_partials.p, (int)L.grid_x, nq, nscen, nm, sc[0].center, sc[nscen > 1 ? 1 : 0].center, 1.0f, L.g.n_paths,
+        d_moments, nq);
     return check_launch(e, "reduce_curve_kernel");
 }
 
@@ -434,8 +519,25 @@ int launch_zbc(hw1f_engine* e, const Launch& L, const ScenDev* sc, int nscen, in
 {
     const int nq = nscen * 5;
     HW_CUDA(e, e->d_partials.ensure((size_t)L.n_runs * L.grid_x * nq));
-    const size_t smem = (size_t)kWinWords * 4 + (size_t)nscen * ((n_steps_S1 + 1) / 2 + 1) * sizeof(float4);
     const dim3 grid(L.grid_x, L.n_runs);
+    if (e->mode == HW1F_MODE_DECOMPOSED) {
+        const FastScen z0 = fast_scen(e, sc[0].sig_st, drift_slot_of(e, sc[0]), n_steps_S1);
+        const FastScen z1 = fast_scen(e, sc[nscen > 1 ? 1 : 0].sig_st, drift_slot_of(e, sc[nscen > 1 ? 1 : 0]), n_steps_S1);
+        const FastTangent tg{0.f, 0.f};
+        const size_t smemf = smem_fast(e, 0);
+        if (nscen == 1) {
+            HW_TRY(set_smem(e, fast_kernel<0, 1, 0>, smemf));
+            fast_kernel<0, 1, 0><<<grid, kThreads, smemf, e->stream>>>(L.g, L.seeds, model_dev(e), z0, z0, z0, z1, z1, tg,
+                                                                      e->d_plans.p, n_steps_S1, L.lead, K, e->d_partials.p);
+        } else {
+            HW_TRY(set_smem(e, fast_kernel<0, 2, 0>, smemf));
+            fast_kernel<0, 2, 0><<<grid, kThreads, smemf, e->stream>>>(L.g, L.seeds, model_dev(e), z0, z0, z0, z1, z1, tg,
+                                                                      e->d_plans.p, n_steps_S1, L.lead, K, e->d_partials.p);
+        }
+        HW_TRY(check_launch(e, "fast_kernel<zbc>"));
+        return reduce_to(e, L.n_runs, L.grid_x, nq, d_moments);
+    }
+    const size_t smem = (size_t)kWinWords * 4 + (size_t)nscen * ((n_steps_S1 + 1) / 2 + 1) * sizeof(float4);
     if (nscen == 1) {
         HW_TRY(set_smem(e, zbc_kernel<1>, smem));
         zbc_kernel<1><<<grid, kThreads, smem, e->stream>>>(L.g, L.seeds, model_dev(e), sc[0], sc[0], e->d_plans.p,
@@ -451,7 +553,17 @@ int launch_zbc(hw1f_engine* e, const Launch& L, const ScenDev* sc, int nscen, in
 
 int launch_pathwise(hw1f_engine* e, const Launch& L, const ScenDev& sc, int n_steps_S1, float K, double* d_moments)
 {
-    HW_CUDA(e, e->d_partials.ensure((size_t)L.n_runs * L.grid_x * 2));
+    HW_CUDA(e, e->d_partials.ensure((size_t)L.n_runs * L.grid_x * 3));
+    if (e->mode == HW1F_MODE_DECOMPOSED) {
+        const FastScen z0 = fast_scen(e, sc.sig_st, drift_slot_of(e, sc), n_steps_S1);
+        const FastTangent tg = fast_tangent(e, n_steps_S1);
+        const size_t smemf = smem_fast(e, 0);
+        HW_TRY(set_smem(e, fast_kernel<0, 0, 1>, smemf));
+        fast_kernel<0, 0, 1><<<dim3(L.grid_x, L.n_runs), kThreads, smemf, e->stream>>>(
+            L.g, L.seeds, model_dev(e), z0, z0, z0, z0, z0, tg, e->d_plans.p, n_steps_S1, L.lead, K, e->d_partials.p);
+        HW_TRY(check_launch(e, "fast_kernel<pathwise>"));
+        return reduce_range(e, L.n_runs, L.grid_x, 3, 0, 2, d_moments, 2);
+    }
     const size_t smem = (size_t)kWinWords * 4 + (size_t)(n_steps_S1 + 1) * sizeof(float4);
     HW_TRY(set_smem(e, pathwise_kernel, smem));
     pathwise_kernel<<<dim3(L.grid_x, L.n_runs), kThreads, smem, e->stream>>>(L.g, L.seeds, model_dev(e), sc,
@@ -517,6 +629,13 @@ int init_kernels(hw1f_engine* e)
     HW_CUDA(e, opt_in(pathwise_kernel, b));
     HW_CUDA(e, opt_in(fused_kernel<false>, b));
     HW_CUDA(e, opt_in(fused_kernel<true>, b));
+    HW_CUDA(e, opt_in(fast_kernel<1, 0, 0>, b));
+    HW_CUDA(e, opt_in(fast_kernel<2, 0, 0>, b));
+    HW_CUDA(e, opt_in(fast_kernel<0, 1, 0>, b));
+    HW_CUDA(e, opt_in(fast_kernel<0, 2, 0>, b));
+    HW_CUDA(e, opt_in(fast_kernel<0, 0, 1>, b));
+    HW_CUDA(e, opt_in(fast_kernel<1, 1, 2>, b));
+    HW_CUDA(e, opt_in(fast_kernel<1, 3, 2>, b));
     HW_CUDA(e, opt_in(zbc_sum_kernel<0>, b));
     HW_CUDA(e, opt_in(zbc_sum_kernel<1>, b));
     HW_CUDA(e, opt_in(zbc_sum_kernel<2>, b));
@@ -634,7 +753,8 @@ int hw1f_engine_destroy(hw1f_engine* e)
     cudaStreamSynchronize(e->stream);
     e->d_Jpow2.release(); e->d_W.release(); e->d_U.release();
     for (auto& d : e->d_drift) d.release();
-    e->d_mkt.release(); e->d_center.release(); e->d_plans.release(); e->d_partials.release(); e->d_moments.release();
+    e->d_mkt.release(); e->d_center.release(); e->d_plans.release();
+    for (auto& d : e->d_emI) d.release(); e->d_partials.release(); e->d_moments.release();
     e->d_out.release(); e->d_int.release();
     if (e->h_stage) cudaFreeHost(e->h_stage);
     if (e->ev0) cudaEventDestroy(e->ev0);
@@ -651,6 +771,21 @@ int hw1f_engine_set_stream(hw1f_engine* e, void* s)
     HW_CUDA(e, cudaSetDevice(e->device));
     HW_CUDA(e, cudaStreamSynchronize(e->stream));
     e->stream = s ? (cudaStream_t)s : e->own_stream;
+    return HW1F_OK;
+}
+
+int hw1f_engine_set_mode(hw1f_engine* e, int mode)
+{
+    if (!e) return HW1F_ERR_INVALID;
+    HW_REQUIRE(e, mode == HW1F_MODE_REFERENCE_ORDER || mode == HW1F_MODE_DECOMPOSED, "unknown mode");
+    e->mode = mode;
+    return HW1F_OK;
+}
+
+int hw1f_engine_get_mode(const hw1f_engine* e, int* mode)
+{
+    if (!e || !mode) return HW1F_ERR_INVALID;
+    *mode = e->mode;
     return HW1F_OK;
 }
 
@@ -1192,6 +1327,30 @@ static int fused_launch(hw1f_engine* e, hw1f_rng* rng, float S1, float S2, float
     HW_TRY(prepare_launch(e, &rng->seed, 1, rng->first_path, rng->n_paths, rng->offset, &L));
     const int nm = e->p.n_mat, next = kFusedExtra + (fd ? kFusedFdExtra : 0), nq = 2 * nm + next;
     HW_CUDA(e, e->d_partials.ensure((size_t)L.grid_x * nq));
+    if (e->mode == HW1F_MODE_DECOMPOSED) {
+        // one noise recursion per stream carries the curve, the base ZBC, both bumped ZBCs and both
+        // tangent twins; the S1 block comes out in the ABI order [ZBC][vega 3][ZBC-][ZBC+]
+        const FastScen c0 = fast_scen(e, sc[0].sig_st, 0, n);
+        const FastScen zm = fd ? fast_scen(e, sc[1].sig_st, 2, n) : c0, zp = fd ? fast_scen(e, sc[2].sig_st, 3, n) : c0;
+        const FastTangent tg = fast_tangent(e, n);
+        const size_t smemf = smem_fast(e, 1);
+        if (fd) {
+            HW_TRY(set_smem(e, fast_kernel<1, 3, 2>, smemf));
+            fast_kernel<1, 3, 2><<<L.grid_x, kThreads, smemf, e->stream>>>(L.g, L.seeds, model_dev(e), c0, c0, c0, zm, zp, tg,
+                                                                          e->d_plans.p, n, 0, K, e->d_partials.p);
+        } else {
+            HW_TRY(set_smem(e, fast_kernel<1, 1, 2>, smemf));
+            fast_kernel<1, 1, 2><<<L.grid_x, kThreads, smemf, e->stream>>>(L.g, L.seeds, model_dev(e), c0, c0, c0, c0, c0, tg,
+                                                                          e->d_plans.p, n, 0, K, e->d_partials.p);
+        }
+        HW_TRY(check_launch(e, "fast_kernel<fused>"));
+        reduce_curve_kernel<<<dim3(nm, 1), 256, 0, e->stream>>>(e->d_partials.p, (int)L.grid_x, nq, 1, nm, c0.emI, c0.emI,
+                                                               2.0f, rng->n_paths, d_moments, nq);
+        HW_TRY(check_launch(e, "reduce_curve_kernel"));
+        HW_TRY(reduce_range(e, 1, L.grid_x, nq, 2 * nm, next, d_moments + 2 * nm, nq));
+        rng->offset += (uint64_t)e->p.n_steps;
+        return HW1F_OK;
+    }
     const size_t smem = (size_t)kWinWords * 4 + (size_t)(e->p.n_steps / 2 + (fd ? 3 : 1) * (n / 2)) * sizeof(float4) +
                         (size_t)nq * sizeof(double) + (size_t)kWarps * 2 * nm * sizeof(float) + (size_t)nm * sizeof(float);
     if (fd) {

@@ -311,7 +311,7 @@ bond_curve_kernel(StreamGeom g, SeedArgs seeds, ModelDev md, ScenDev sc0, ScenDe
     const int half = md.stride >> 1;
     // lane 0 stores the sum, lane 16 the sum of squares (see warp_sum_pair)
     const bool writer = (lane & 15) == 0;
-    const int woff = warp * nq + ((lane & 16) ? n_mat : 0);
+    float* const wrow = wflt + warp * nq + ((lane & 16) ? n_mat : 0);
 
     for (unsigned long long chunk = blockIdx.x; chunk < g.n_chunks; chunk += gridDim.x) {
         ThreadStreams t = derive_streams(g, seeds, run, chunk, win);   // contains the __syncthreads()
@@ -348,7 +348,7 @@ bond_curve_kernel(StreamGeom g, SeedArgs seeds, ModelDev md, ScenDev sc0, ScenDe
                 float2 dv = add2(p0, splat(-cen[s * n_mat + m]));
                 if (!full) dv = mul2(dv, make_float2(mA, mB));   // block-uniform branch: ragged edge chunks only
                 const float keep = warp_sum_pair(add_(dv.x, dv.y), fma_(dv.x, dv.x, mul_(dv.y, dv.y)), lane);
-                if (writer) wflt[woff + s * nq1 + m] = keep;
+                if (writer) wrow[s * nq1 + m] = keep;
             }
         }
         __syncthreads();
@@ -559,15 +559,17 @@ pathwise_kernel(StreamGeom g, SeedArgs seeds, ModelDev md, ScenDev sc, const Bon
 // =================================================================================================
 // second level of the deterministic tree: moments[run][q] = sum over blocks (fixed order, double)
 // =================================================================================================
+// partials[run][block][stride]; sums entries q = 0..gridDim.x-1 -> moments[run*out_stride + q]
 template <class T>
 __global__ void __launch_bounds__(256)
-reduce_partials_kernel(const T* __restrict__ partials, int n_blocks, int nq, double* __restrict__ moments)
+reduce_partials_kernel(const T* __restrict__ partials, int n_blocks, int stride, double* __restrict__ moments,
+                       int out_stride)
 {
     __shared__ double sh[256];
     const int q = blockIdx.x, run = blockIdx.y, tid = threadIdx.x;
-    const T* p = partials + (size_t)run * n_blocks * nq + q;
+    const T* p = partials + (size_t)run * n_blocks * stride + q;
     double acc = 0.0;
-    for (int b = tid; b < n_blocks; b += 256) acc += (double)p[(size_t)b * nq];
+    for (int b = tid; b < n_blocks; b += 256) acc += (double)p[(size_t)b * stride];
     sh[tid] = acc;
     __syncthreads();
 #pragma unroll
@@ -575,25 +577,26 @@ reduce_partials_kernel(const T* __restrict__ partials, int n_blocks, int nq, dou
         if (tid < o) sh[tid] += sh[tid + o];
         __syncthreads();
     }
-    if (tid == 0) moments[(size_t)run * nq + q] = sh[0];
+    if (tid == 0) moments[(size_t)run * out_stride + q] = sh[0];
 }
 
-// curve variant: block (m, run*NSCEN+s) sums sum_d and sum_d2 of maturity m and undoes the centring:
+// curve variant: block (m, run*NSCEN+s) sums sum_d and sum_d2 of maturity m and undoes the centring
+// with c_m = center_scale * center[m]:
 //   sum p0 = sum d + n c,   sum p0^2 = sum d^2 + 2 c sum d + n c^2      (double)
+// partials[run][block][stride] with the curve block of scenario s at offset s*2*n_mat
 __global__ void __launch_bounds__(256)
-reduce_curve_kernel(const double* __restrict__ partials, int n_blocks, int nscen, int n_mat,
-                    const float* __restrict__ center0, const float* __restrict__ center1,
-                    unsigned long long n_local, double* __restrict__ moments)
+reduce_curve_kernel(const double* __restrict__ partials, int n_blocks, int stride, int nscen, int n_mat,
+                    const float* __restrict__ center0, const float* __restrict__ center1, float center_scale,
+                    unsigned long long n_local, double* __restrict__ moments, int out_stride)
 {
     __shared__ double sh[2][256];
     const int m = blockIdx.x, rs = blockIdx.y, tid = threadIdx.x;
     const int run = rs / nscen, s = rs % nscen;
-    const int nq = nscen * 2 * n_mat;
-    const double* p = partials + (size_t)run * n_blocks * nq + (size_t)s * 2 * n_mat + m;
+    const double* p = partials + (size_t)run * n_blocks * stride + (size_t)s * 2 * n_mat + m;
     double a = 0.0, b = 0.0;
     for (int blk = tid; blk < n_blocks; blk += 256) {
-        a += p[(size_t)blk * nq];
-        b += p[(size_t)blk * nq + n_mat];
+        a += p[(size_t)blk * stride];
+        b += p[(size_t)blk * stride + n_mat];
     }
     sh[0][tid] = a;
     sh[1][tid] = b;
@@ -604,10 +607,10 @@ reduce_curve_kernel(const double* __restrict__ partials, int n_blocks, int nscen
         __syncthreads();
     }
     if (tid == 0) {
-        double* out = moments + (size_t)run * nq + (size_t)s * 2 * n_mat;
+        double* out = moments + (size_t)run * out_stride + (size_t)s * 2 * n_mat;
         if (m == 0) { out[0] = 0.0; out[n_mat] = 0.0; }
         else {
-            const double c = (double)(s ? center1 : center0)[m], n = (double)n_local;
+            const double c = (double)center_scale * (double)(s ? center1 : center0)[m], n = (double)n_local;
             const double sd = sh[0][0], sdd = sh[1][0];
             out[m] = sd + n * c;
             out[n_mat + m] = sdd + 2.0 * c * sd + n * c * c;

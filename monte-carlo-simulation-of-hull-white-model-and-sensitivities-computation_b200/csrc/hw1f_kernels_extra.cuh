@@ -191,7 +191,7 @@ fused_kernel(StreamGeom g, SeedArgs seeds, ModelDev md, ScenDev sc, ScenDev scm,
     const int half = md.stride >> 1;
     const int m_S1 = n_steps_S1 / md.stride;          // maturity index reached at S1
     const bool writer = (lane & 15) == 0;
-    const int woff = warp * 2 * n_mat + ((lane & 16) ? n_mat : 0);
+    float* const wrow = wflt + warp * 2 * n_mat + ((lane & 16) ? n_mat : 0);
 
     for (unsigned long long chunk = blockIdx.x; chunk < g.n_chunks; chunk += gridDim.x) {
         ThreadStreams t = derive_streams(g, seeds, 0, chunk, win);
@@ -243,7 +243,7 @@ fused_kernel(StreamGeom g, SeedArgs seeds, ModelDev md, ScenDev sc, ScenDev scm,
             float2 dv = add2(p0, splat(-cen[m]));
             if (!full) dv = mul2(dv, mask);
             const float keep = warp_sum_pair(add_(dv.x, dv.y), fma_(dv.x, dv.x, mul_(dv.y, dv.y)), lane);
-            if (writer) wflt[woff + m] = keep;
+            if (writer) wrow[m] = keep;
         };
 
         int pair = 0;

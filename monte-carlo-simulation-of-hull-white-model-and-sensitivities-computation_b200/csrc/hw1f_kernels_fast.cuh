@@ -1,0 +1,225 @@
+// hw1f_kernels_fast.cuh -- "decomposed" simulation kernels (engine mode HW1F_MODE_DECOMPOSED).
+//
+// The exact discretisation is linear in the Gaussian shocks, so every path this engine ever needs
+// from one stream of normals -- the +G / -G antithetic twins, the sigma -/+ eps bumped twins, the
+// pathwise tangent d(r)/d(sigma) -- is  (deterministic part) +/- (scale) * h  with ONE shared
+// noise recursion per stream:
+//
+//     h_{i+1} = h_i e^{-a dt} + G_i ,   S_n = sum_{i<=n} h_i ,   q_n = 2 S_n - h_n
+//     r(+/-)  = m_i      +/- sig_st h_i          (m: noise-free short rate, host table, double)
+//     I(+/-)  = Im_i     +/- (dt/2) sig_st q_i   (trapezoid of the noise part: sum (h_i + h_{i+1}))
+//     tangent = D_i      + (sig_st/sigma) h_i ,  its integral = ID_i + (dt/2)(sig_st/sigma) q_i
+//
+// Two packed FP32 instructions per time step for BOTH antithetic twins of BOTH lanes (and for any
+// number of sigma scenarios), instead of eight.  Same XORWOW integers and same Box-Muller floats as
+// the reference-order kernels; the per-path floats differ from the reference by rounding only
+// (~1e-7 relative), far inside the 1e-5 north-star tolerance -- tests run both modes against the
+// oracle and against the reference binaries.
+#pragma once
+#include "hw1f_kernels_extra.cuh"
+
+namespace hw1f {
+
+// per sigma-scenario constants of the decomposed form
+struct FastScen {
+    float sg;       // sig_st
+    float c;        // 0.5 * dt * sig_st
+    float mS1;      // noise-free short rate at S1
+    float ImS1;     // noise-free integral at S1
+    const float* emI;   // [n_mat] exp(-Im) at the save points (curve kernels)
+};
+struct FastTangent {
+    float DS1, IDS1;    // noise-free tangent and its integral at S1
+};
+
+struct FastState {
+    float2 h, S;
+    __device__ __forceinline__ float2 q() const { return fma2(S, splat(2.0f), make_float2(-h.x, -h.y)); }
+};
+
+// NCUR  : number of curve scenarios accumulated on the maturity grid (0, 1, 2)
+// NZBC  : number of ZBC scenarios evaluated at S1 (0..3); plans[0..NZBC)
+// PW    : 0 none, 1 pathwise vega of the +G path only (the reference's estimator), 2 both twins
+// partials[run][block][NCUR*2*n_mat + NZBC*5 + (PW ? 3 : 0)] doubles; the S1 block is laid out as
+// [ZBC scenario 0 (5)] [pathwise (3)] [ZBC scenarios 1.. (5 each)]  == the hw1f_fused* ABI order
+template <int NZBC, int PW>
+__device__ __forceinline__ constexpr int ext_zbc(int s) { return s == 0 ? 0 : 5 + (PW ? 3 : 0) + 5 * (s - 1); }
+template <int NZBC, int PW>
+__device__ __forceinline__ constexpr int ext_pw() { return NZBC > 0 ? 5 : 0; }
+
+template <int NCUR, int NZBC, int PW>
+__global__ void __launch_bounds__(kThreads, (NZBC + PW >= 3 ? 3 : 5))
+fast_kernel(StreamGeom g, SeedArgs seeds, ModelDev md, FastScen cs0, FastScen cs1, FastScen zs0, FastScen zs1,
+            FastScen zs2, FastTangent tg, const BondPlan* __restrict__ plans, int n_steps_S1, int lead, float K,
+            double* __restrict__ partials)
+{
+    extern __shared__ __align__(16) uint32_t smem[];
+    constexpr int kS1 = NZBC * 5 + (PW ? 3 : 0);
+    const int n_mat = md.n_mat;
+    const int nqc = NCUR * 2 * n_mat;
+    const int nq = nqc + kS1;
+    uint32_t* win = smem;
+    double* bacc = reinterpret_cast<double*>(smem + kWinWords);                  // [nqc]
+    float* wflt = reinterpret_cast<float*>(bacc + (NCUR ? nqc : 0));            // [kWarps][nqc]
+    float* emI = wflt + (NCUR ? kWarps * nqc : 0);                              // [NCUR][n_mat]
+    __shared__ double wext[kWarps][kS1 > 0 ? kS1 : 1];
+    __shared__ double bext[kS1 > 0 ? kS1 : 1];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int run = blockIdx.y;
+
+    if (NCUR) {
+        for (int k = tid; k < nqc; k += kThreads) bacc[k] = 0.0;
+        for (int k = tid; k < kWarps * nqc; k += kThreads) wflt[k] = 0.0f;
+        for (int k = tid; k < n_mat; k += kThreads) {
+            emI[k] = cs0.emI[k];
+            if (NCUR > 1) emI[n_mat + k] = cs1.emI[k];
+        }
+    }
+    if (kS1 > 0 && tid < kS1) bext[tid] = 0.0;
+
+    const float2 e2 = splat(md.exp_adt);
+    const int half = md.stride >> 1;
+    const int n_total = NCUR ? md.n_steps : n_steps_S1;
+    const int m_S1 = NCUR ? n_steps_S1 / md.stride : 0;
+    // lanes 0 / 16 of each warp own the (sum, sum of squares) slots of that warp's row
+    const bool writer = (lane & 15) == 0;
+    float* const wrow = wflt + warp * nqc + ((lane & 16) ? n_mat : 0);
+    // per-scenario exponents: exp(-/+ c q) = ex2(-/+ q * (c log2e))
+    const float kc0 = mul_(cs0.c, kLog2e), kc1 = mul_(cs1.c, kLog2e);
+
+    for (unsigned long long chunk = blockIdx.x; chunk < g.n_chunks; chunk += gridDim.x) {
+        ThreadStreams t = derive_streams(g, seeds, run, chunk, win);
+        FastState st;
+        st.h = splat(0.0f);
+        st.S = splat(0.0f);
+        const float2 mask = make_float2(t.validA ? 1.0f : 0.0f, t.validB ? 1.0f : 0.0f);
+        const bool full = __syncthreads_and(t.validA && t.validB);
+
+        auto step1 = [&](float2 G) {
+            st.h = fma2(st.h, e2, G);
+            st.S = add2(st.S, st.h);
+        };
+        auto pairfn = [&](int, float2 ns, float2 nc) { step1(ns); step1(nc); };
+
+        auto save_curve = [&](int m) {
+            const float2 q = st.q();
+#pragma unroll
+            for (int s = 0; s < NCUR; ++s) {
+                // p0 = e^{-I+} + e^{-I-} = e^{-Im} (e^{-c q} + e^{+c q});  centred: d = p0 - 2 e^{-Im}
+                const float2 y = mul2(q, splat(s ? kc1 : kc0));
+                const float2 ep = make_float2(mufu_ex2(y.x), mufu_ex2(y.y));
+                const float2 en = make_float2(mufu_ex2(-y.x), mufu_ex2(-y.y));
+                float2 dv = mul2(add2(add2(ep, en), splat(-2.0f)), splat(emI[s * n_mat + m]));
+                if (!full) dv = mul2(dv, mask);
+                const float keep = warp_sum_pair(add_(dv.x, dv.y), fma_(dv.x, dv.x, mul_(dv.y, dv.y)), lane);
+                if (writer) wrow[s * 2 * n_mat + m] = keep;
+            }
+        };
+
+        auto eval_S1 = [&]() {
+            const float2 q = st.q();
+            const double mA = t.validA ? 1.0 : 0.0, mB = t.validB ? 1.0 : 0.0;
+#pragma unroll
+            for (int s = 0; s < NZBC; ++s) {
+                const FastScen z = (s == 0) ? zs0 : (s == 1 ? zs1 : zs2);
+                PairState ps;
+                const float2 dr = mul2(st.h, splat(z.sg)), dI = mul2(q, splat(z.c));
+                ps.r1 = add2(splat(z.mS1), dr);
+                ps.r2 = add2(splat(z.mS1), make_float2(-dr.x, -dr.y));
+                ps.I1 = add2(splat(z.ImS1), dI);
+                ps.I2 = add2(splat(z.ImS1), make_float2(-dI.x, -dI.y));
+                float2 x1, x2, c1, c2;
+                zbc_payoffs(ps, plans[s], K, x1, x2, c1, c2);
+                const float2 mom5[5] = {add2(x1, x2), add2(c1, c2), fma2(x1, x1, mul2(x2, x2)),
+                                        fma2(c1, c1, mul2(c2, c2)), fma2(c1, x1, mul2(c2, x2))};
+#pragma unroll
+                for (int k = 0; k < 5; ++k) {
+                    const double w = warp_sum((double)mom5[k].x * mA + (double)mom5[k].y * mB);
+                    if (lane == 0) wext[warp][ext_zbc<NZBC, PW>(s) + k] = w;
+                }
+            }
+            if (PW) {
+                const BondPlan pl = plans[0];
+                const FastScen z = zs0;
+                const float2 dr = mul2(st.h, splat(z.sg)), dI = mul2(q, splat(z.c));
+                const float2 dt_ = mul2(st.h, splat(pl.c_t));                       // tangent noise
+                const float2 dJ = mul2(q, splat(mul_(mul_(0.5f, md.dt), pl.c_t)));   // its integral
+                auto vega_of = [&](float sgn) {
+                    const float2 r = fma2(splat(sgn), dr, splat(z.mS1));
+                    const float2 I = fma2(splat(sgn), dI, splat(z.ImS1));
+                    const float2 tgv = fma2(splat(sgn), dt_, splat(tg.DS1));
+                    const float2 J = fma2(splat(sgn), dJ, splat(tg.IDS1));
+                    const float2 zz0 = mul2(mul2(r, splat(pl.negB)), splat(kLog2e));
+                    const float2 P = mul2(splat(pl.A), make_float2(mufu_ex2(zz0.x), mufu_ex2(zz0.y)));
+                    const float2 qq = mul2(I, splat(-kLog2e));
+                    const float2 disc = make_float2(mufu_ex2(qq.x), mufu_ex2(qq.y));
+                    const float2 inner = fma2(splat(pl.xk), splat(pl.B), tgv);
+                    float2 term1 = mul2(disc, mul2(mul2(P, splat(pl.negB)), inner));
+                    if (!(P.x > K)) term1.x = 0.0f;
+                    if (!(P.y > K)) term1.y = 0.0f;
+                    const float2 gk = add2(P, splat(-K));
+                    const float2 payoff = make_float2(fmaxf(0.0f, gk.x), fmaxf(0.0f, gk.y));
+                    const float2 zz = mul2(disc, J);
+                    return fma2(payoff, make_float2(-zz.x, -zz.y), term1);
+                };
+                const float2 v1 = vega_of(1.0f);
+                double e0, e1, e2;
+                if (PW == 1) {   // the reference's non-antithetic estimator: sum v, sum v^2 over +G paths
+                    const double a = (double)v1.x * mA, b = (double)v1.y * mB;
+                    e0 = a + b; e1 = a * a + b * b; e2 = e0;
+                } else {         // both twins: sum (v1+v2), sum (v1+v2)^2, sum v1
+                    const float2 v2 = vega_of(-1.0f);
+                    const double a = ((double)v1.x + (double)v2.x) * mA, b = ((double)v1.y + (double)v2.y) * mB;
+                    e0 = a + b; e1 = a * a + b * b; e2 = (double)v1.x * mA + (double)v1.y * mB;
+                }
+                const double w0 = warp_sum(e0), w1 = warp_sum(e1), w2 = warp_sum(e2);
+                if (lane == 0) { wext[warp][ext_pw<NZBC, PW>()] = w0; wext[warp][ext_pw<NZBC, PW>() + 1] = w1; wext[warp][ext_pw<NZBC, PW>() + 2] = w2; }
+            }
+        };
+
+        int pair = 0;
+        if (NCUR) {
+            for (int m = 1; m < n_mat; ++m) {
+                advance_pairs(t, pair, half, pairfn);
+                save_curve(m);
+                if (kS1 > 0 && m == m_S1) eval_S1();
+            }
+        } else {
+            const int n_main = n_total - lead;
+            if (lead && n_total > 0) {   // cached cos-branch normal of the pair the previous launch opened
+                float2 ns, nc;
+                one_pair(t, ns, nc);
+                step1(nc);
+            }
+            advance_pairs(t, pair, n_main >> 1, pairfn);
+            if (n_main & 1) {            // odd tail: sin branch only
+                float2 ns, nc;
+                one_pair(t, ns, nc);
+                step1(ns);
+            }
+            eval_S1();
+        }
+        __syncthreads();
+        if (NCUR) {
+            for (int k = tid; k < nqc; k += kThreads) {
+                double acc = (double)wflt[k];
+#pragma unroll
+                for (int w = 1; w < kWarps; ++w) acc += (double)wflt[w * nqc + k];
+                bacc[k] += acc;
+            }
+        }
+        if (kS1 > 0 && tid < kS1) {
+            double acc = wext[0][tid];
+#pragma unroll
+            for (int w = 1; w < kWarps; ++w) acc += wext[w][tid];
+            bext[tid] += acc;
+        }
+    }
+    __syncthreads();
+    double* out = partials + ((size_t)run * gridDim.x + blockIdx.x) * nq;
+    if (NCUR)
+        for (int k = tid; k < nqc; k += kThreads) out[k] = bacc[k];
+    if (kS1 > 0 && tid < kS1) out[nqc + tid] = bext[tid];
+}
+
+}  // namespace hw1f

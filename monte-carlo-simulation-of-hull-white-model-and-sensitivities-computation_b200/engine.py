@@ -134,6 +134,16 @@ class Engine:
         """cuda_stream: integer cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream) or None."""
         self._check(self._lib.hw1f_engine_set_stream(self._h, C.c_void_p(cuda_stream or 0)))
 
+    def set_mode(self, mode):
+        """_ffi.MODE_REFERENCE_ORDER (per-path reference float sequence) or _ffi.MODE_DECOMPOSED (default)"""
+        self._check(self._lib.hw1f_engine_set_mode(self._h, int(mode)))
+
+    @property
+    def mode(self):
+        m = C.c_int()
+        self._lib.hw1f_engine_get_mode(self._h, C.byref(m))
+        return m.value
+
     def synchronize(self):
         self._check(self._lib.hw1f_engine_synchronize(self._h))
 

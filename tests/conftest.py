@@ -45,9 +45,11 @@ def hw():
     return hw1f_b200
 
 
-@pytest.fixture(scope="session")
-def engine(hw):
+@pytest.fixture(scope="session", params=["decomposed", "reference_order"])
+def engine(hw, request):
+    """every GPU parity test runs in both simulation modes (include/hw1f.h: HW1F_MODE_*)"""
     eng = hw.Engine(device=0)
+    eng.set_mode(hw._ffi.MODE_DECOMPOSED if request.param == "decomposed" else hw._ffi.MODE_REFERENCE_ORDER)
     yield eng
     eng.close()
 

@@ -278,11 +278,13 @@ def test_grid_stride_chunks_large_run(engine, hw, curve):
     dict(n_steps=600, n_mat=51, T_final=6.0),                      # stride 12, dt = 0.01, spacing 0.12
     dict(a=0.5, sigma=0.2, r0=0.03, theta_a0=0.02, theta_b0=0.001, theta_a1=0.03, theta_b1=-0.0005, theta_break=4.0),
 ])
-def test_other_model_parameters(hw, over):
+@pytest.mark.parametrize("mode", [0, 1])
+def test_other_model_parameters(hw, over, mode):
     """the engine is not specialised to the reference's macros (common.cuh:16-39)"""
     from oracle_lib import Oracle
     o = Oracle(**over)
     eng = hw.Engine(device=0, params=hw.default_params(**over))
+    eng.set_mode(mode)
     try:
         n = 1 << 12
         c = eng.bond_curve(hw.Rng(31337, n))
