@@ -41,6 +41,8 @@ struct Engine {
         int dev = -1;   // select_gpu(): most free memory; HW_DEVICE overrides
         if (const char* s = std::getenv("HW_DEVICE")) dev = std::atoi(s);
         require(hw1f_engine_create(dev, &h), nullptr, "hw1f_engine_create");
+        if (const char* s = std::getenv("HW_MODE"))   // "reference": the reference's own per-path float order
+            hw1f_engine_set_mode(h, (s[0] == 'r' || s[0] == '0') ? HW1F_MODE_REFERENCE_ORDER : HW1F_MODE_DECOMPOSED);
         hw1f_default_params(&p);
         require(hw1f_set_model(h, &p), h, "hw1f_set_model");
         hw1f_get_constants(h, &c);
