@@ -185,7 +185,10 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        import datetime
+        # a short watchdog: a mismatched collective should fail in minutes, not hang the box
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank),
+                                timeout=datetime.timedelta(seconds=180))
     dev = torch.device("cuda", local_rank)
 
     def barrier():
@@ -265,6 +268,23 @@ def main():
     sampler.stop()
     clocks = sampler.summary(t_load0, t_load2)
 
+    # the same steps in the other arithmetic mode, for transparency (device-timed).  EVERY rank runs
+    # this loop: device_step contains the all-reduce
+    other = "reference_order" if args.mode == "decomposed" else "decomposed"
+    eng.set_mode(hw._ffi.MODE_REFERENCE_ORDER if other == "reference_order" else hw._ffi.MODE_DECOMPOSED)
+    for i in range(3):
+        device_step(1000 + i)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n_other = min(args.steps, 50)
+    e0.record()
+    for i in range(n_other):
+        device_step(5000 + i)
+    e1.record()
+    torch.cuda.synchronize()
+    other_ms = e0.elapsed_time(e1) / n_other
+    eng.set_mode(hw._ffi.MODE_DECOMPOSED if args.mode == "decomposed" else hw._ffi.MODE_REFERENCE_ORDER)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -284,21 +304,6 @@ def main():
     xu_frac = per_gpu * algo["xu"] / mufu
     issue_frac = per_gpu * algo["issue"] / issue_peak
     bound = "xu" if xu_frac >= issue_frac else "issue"
-    # the same steps in the other arithmetic mode, for transparency (device-timed)
-    other = "reference_order" if args.mode == "decomposed" else "decomposed"
-    eng.set_mode(hw._ffi.MODE_REFERENCE_ORDER if other == "reference_order" else hw._ffi.MODE_DECOMPOSED)
-    for i in range(3):
-        device_step(1000 + i)
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    n_other = min(args.steps, 50)
-    e0.record()
-    for i in range(n_other):
-        device_step(5000 + i)
-    e1.record()
-    torch.cuda.synchronize()
-    other_ms = e0.elapsed_time(e1) / n_other
-    eng.set_mode(hw._ffi.MODE_DECOMPOSED if args.mode == "decomposed" else hw._ffi.MODE_REFERENCE_ORDER)
     roofline = {
         # this path is bound by the SFU (XU) pipe and by instruction issue, not by HBM or tensor cores
         # (SURVEY 8d); "achieved"/"peak" are for the binding resource, the other one is given beside it
