@@ -246,6 +246,7 @@ int hw1f_multi_destroy(hw1f_multi* m);
 int hw1f_multi_device_count(const hw1f_multi* m, int* n_gpus);
 const char* hw1f_multi_last_error(const hw1f_multi* m);
 int hw1f_multi_set_model(hw1f_multi* m, const hw1f_params* p);
+int hw1f_multi_set_mode(hw1f_multi* m, int mode);   /* HW1F_MODE_* on every device */
 int hw1f_multi_bond_curve(hw1f_multi* m, uint64_t seed, uint64_t n_paths_total, uint64_t normal_offset,
                           float* P, float* f, float* P_se, float* wall_ms);
 int hw1f_multi_zbc_cv(hw1f_multi* m, uint64_t seed, uint64_t n_paths_total, uint64_t normal_offset,

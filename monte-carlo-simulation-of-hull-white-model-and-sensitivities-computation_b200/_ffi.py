@@ -111,6 +111,7 @@ SYMBOLS = {
     "hw1f_multi_device_count": (C.c_int, [_P, C.POINTER(C.c_int)]),
     "hw1f_multi_last_error": (C.c_char_p, [_P]),
     "hw1f_multi_set_model": (C.c_int, [_P, C.POINTER(Params)]),
+    "hw1f_multi_set_mode": (C.c_int, [_P, C.c_int]),
     "hw1f_multi_bond_curve": (C.c_int, [_P, C.c_uint64, C.c_uint64, C.c_uint64, _P, _P, _P, _F]),
     "hw1f_multi_zbc_cv": (C.c_int, [_P, C.c_uint64, C.c_uint64, C.c_uint64, C.c_float, C.c_float, C.c_float, _P, _P,
                                     C.c_int32, C.POINTER(ZbcResult)]),

@@ -188,6 +188,13 @@ int hw1f_multi_device_count(const hw1f_multi* m, int* n)
     return HW1F_OK;
 }
 
+int hw1f_multi_set_mode(hw1f_multi* m, int mode)
+{
+    if (!m) return HW1F_ERR_INVALID;
+    for (int d = 0; d < m->n; ++d) M_ENG(m, d, hw1f_engine_set_mode(m->eng[d], mode));
+    return HW1F_OK;
+}
+
 int hw1f_multi_set_model(hw1f_multi* m, const hw1f_params* p)
 {
     if (!m || !p) return HW1F_ERR_INVALID;

@@ -31,6 +31,9 @@ int main()
         if (hw1f_multi_create(gpus, &m) != HW1F_OK) { std::fprintf(stderr, "hw1f_multi_create failed\n"); return 1; }
         uint64_t seed = 0;
         hw1f_rng_info(rng.h, &seed, nullptr, nullptr);
+        int mode = HW1F_MODE_DECOMPOSED;
+        hw1f_engine_get_mode(eng.h, &mode);
+        hw1f_multi_set_mode(m, mode);
         if (hw1f_multi_set_model(m, &p) != HW1F_OK ||
             hw1f_multi_bond_curve(m, seed, kNPaths, 0, P.data(), f.data(), se.data(), &sim_ms) != HW1F_OK) {
             std::fprintf(stderr, "multi-GPU run failed: %s\n", hw1f_multi_last_error(m));

@@ -9,7 +9,7 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.fixture(scope="module")
-def multi(hw):
+def multi(hw, engine):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs at least 2 GPUs")
     lib = hw._ffi.load()
@@ -17,6 +17,7 @@ def multi(hw):
     assert lib.hw1f_multi_create(2, C.byref(h)) == 0
     p = hw.default_params()
     assert lib.hw1f_multi_set_model(h, C.byref(p)) == 0, lib.hw1f_multi_last_error(h)
+    assert lib.hw1f_multi_set_mode(h, engine.mode) == 0      # same arithmetic mode as the single-GPU engine
     yield lib, h
     lib.hw1f_multi_destroy(h)
 
