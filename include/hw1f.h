@@ -20,7 +20,9 @@
  *     curand_init(seed, first_path + p, 0, &st) + curand_normal(&st) would deliver
  *     (include/common.cuh:277-280, :327), starting at the handle's normal offset.
  *     No per-path state array exists; the state is re-derived inside the kernels.
- *   - there is NO CPU fallback: without a CUDA device every compute call fails.
+ *   - there is NO CPU fallback: without a CUDA device every compute call fails;
+ *   - an engine owns one stream and scratch buffers: it is not thread-safe.  Use one engine
+ *     per host thread (engines on the same device share nothing but the GPU).
  */
 #ifndef HW1F_H
 #define HW1F_H

@@ -1041,7 +1041,7 @@ int hw1f_zbc_cv_finish(hw1f_engine* e, const double* d_moments, uint64_t n_paths
     HW_CUDA(e, cudaSetDevice(e->device));
     double mom[5];
     HW_TRY(download(e, mom, d_moments, sizeof(mom)));
-    zbc_algebra(mom, n_paths_total, P0S2, out->n_steps_S1, out);
+    zbc_algebra(mom, n_paths_total, P0S2, 0, out);   // the step count is not part of the moments
     return HW1F_OK;
 }
 

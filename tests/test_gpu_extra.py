@@ -172,3 +172,32 @@ def test_fused_with_fd_bumps_one_launch(engine, hw, curve):
     pw = engine.vega_pathwise(hw.Rng(SEED, N), curve["P"], curve["f"], n_steps_S1=500)
     assert abs(got["vega"]["vega_pathwise_f64"] - pw["vega_pathwise_f64"]) < 4 * pw["vega_pathwise_se"]
     assert 0 < got["vega"]["vega_pathwise_se"] < pw["vega_pathwise_se"]      # antithetic twins: smaller error
+
+
+def test_engine_lifecycle_and_argument_errors(hw, curve):
+    """create/destroy repeatedly, bad arguments come back as status codes, never as a crash or exit()"""
+    import ctypes as C
+    lib = hw._ffi.load()
+    free0 = torch.cuda.mem_get_info()[0]
+    for k in range(6):
+        e = hw.Engine(device=0)
+        e.set_mode(k % 2)
+        c = e.bond_curve(hw.Rng(k, 3000 + k))
+        # P(0,0) = (2N) * MUFU.RCP((float)2N) like the reference's epilogue: exactly 1 only for powers of two
+        assert abs(c["P"][0] - 1.0) < 2e-7 and np.isfinite(c["f"]).all()
+        e.close()
+    assert torch.cuda.mem_get_info()[0] > free0 - (64 << 20)          # nothing substantial leaked
+    e = hw.Engine(device=0)
+    try:
+        assert lib.hw1f_bond_curve(e._h, None, None, None, None, None) == hw._ffi.ERR_INVALID
+        assert lib.hw1f_engine_set_mode(e._h, 7) == hw._ffi.ERR_INVALID
+        bad = hw.default_params(n_steps=1000, n_mat=77)                # 1000 % 76 != 0 (common.cuh:25-27)
+        assert lib.hw1f_set_model(e._h, C.byref(bad)) == hw._ffi.ERR_INVALID
+        assert b"divisible" in lib.hw1f_last_error(e._h)
+        with pytest.raises(hw.HW1FError):
+            e.sample_paths(hw.Rng(1, 8), 32)                           # more paths than the handle owns
+        assert abs(e.bond_curve(hw.Rng(1, 777))["P"][0] - 1.0) < 2e-7  # still healthy
+    finally:
+        e.close()
+    h = C.c_void_p()
+    assert lib.hw1f_engine_create(99, C.byref(h)) == hw._ffi.ERR_NO_DEVICE
