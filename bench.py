@@ -161,6 +161,8 @@ def main():
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--paths-log2", type=int, default=N_PATHS_LOG2, help="subsequences per GPU (default 2^20)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--collective", default="peer", choices=["peer", "nccl"],
+                    help="moment all-reduce for N > 1: own NVLink peer-memory kernel (hw1f_comm_*) or NCCL")
     ap.add_argument("--mode", default="decomposed", choices=["decomposed", "reference_order"],
                     help="simulation arithmetic (include/hw1f.h HW1F_MODE_*); both give the same Gaussians")
     args = ap.parse_args()
@@ -208,18 +210,41 @@ def main():
     moments = torch.zeros(2 * n_mat, dtype=torch.float64, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
+    # the single collective of the path: 202 doubles.  Default: the engine's own peer-memory kernel over
+    # NVLink (rank-ordered, bit-identical on all ranks); NCCL if asked for or if CUDA IPC is unavailable.
+    peer, collective = None, "none"
+    if world > 1:
+        collective = "nccl"
+        want_peer = torch.tensor([1 if args.collective == "peer" else 0], device=dev)
+        if args.collective == "peer":
+            try:
+                peer = hw.package.parallel.PeerAllReduce(eng, stream)
+            except Exception as exc:                   # noqa: BLE001
+                print(f"[rank {rank}] peer all-reduce unavailable ({exc}); using NCCL", file=sys.stderr)
+                want_peer[0] = 0
+        dist.all_reduce(want_peer, op=dist.ReduceOp.MIN)   # all ranks or none
+        if int(want_peer.item()) == 1:
+            collective = "peer_nvlink_kernel"
+        elif peer is not None:
+            peer.close()
+            peer = None
+
+    def reduce_moments():
+        if peer is not None:
+            peer.all_reduce(moments)
+        elif world > 1:
+            dist.all_reduce(moments)
+
     def device_step(seed):
         rng = hw.Rng(seed, n_paths, first_path=first_path)
         eng.bond_curve_moments(rng, moments.data_ptr())
-        if world > 1:
-            dist.all_reduce(moments)                 # the single collective of the path: 202 doubles
+        reduce_moments()
 
     def e2e_step(seed):
         eng.set_model(eng.params)                    # compute_constants(): H2D of the model tables
         rng = hw.Rng(seed, n_paths, first_path=first_path)
         eng.bond_curve_moments(rng, moments.data_ptr())
-        if world > 1:
-            dist.all_reduce(moments)
+        reduce_moments()
         return eng.bond_curve_finish(moments.data_ptr(), n_paths * world)   # D2H of P, f, P_se
 
     sampler = ClockSampler(local_rank)
@@ -243,7 +268,7 @@ def main():
         flush.zero_()
     barrier()
     t_load1 = time.time()
-    launches = eng.launch_count - launches0
+    launches = eng.launch_count - launches0 + (args.steps if peer is not None else 0)
     step_ms = [a.elapsed_time(b) for a, b in ev]
     total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
     if world > 1:
@@ -267,6 +292,16 @@ def main():
     e2e_value = path_steps_per_step / (e2e_ms * 1e-3)
     sampler.stop()
     clocks = sampler.summary(t_load0, t_load2)
+
+    collective_check = None
+    if peer is not None:   # same local moments through both collectives (every rank takes part)
+        eng.bond_curve_moments(hw.Rng(424242, n_paths, first_path=first_path), moments.data_ptr())
+        via_nccl = moments.clone()
+        peer.all_reduce(moments)
+        dist.all_reduce(via_nccl)
+        torch.cuda.synchronize()
+        rel = float(((moments - via_nccl).abs() / (via_nccl.abs() + 1e-300)).max())
+        collective_check = {"max_rel_diff_vs_nccl": rel, "timeouts": peer.timeouts()}
 
     # the same steps in the other arithmetic mode, for transparency (device-timed).  EVERY rank runs
     # this loop: device_step contains the all-reduce

@@ -258,6 +258,25 @@ int hw1f_multi_vega_pathwise(hw1f_multi* m, uint64_t seed, uint64_t n_paths_tota
                              float S1, float S2, float K, const float* P_mkt, const float* f_mkt,
                              int32_t n_steps_S1, double* vega, double* vega_se);
 
+/* ---- peer-memory all-reduce (one process per GPU) ------------------------------------------------ */
+/* The path's single exchange step -- summing the packed double moment vector over ranks -- as ONE own
+ * kernel over NVLink peer memory instead of an NCCL call: every rank posts its vector into a mailbox
+ * of every peer (CUDA IPC mapping), raises a system-scope flag, waits (bounded) for the peers' flags
+ * and sums the slots in rank order, so the result is bit-identical on all ranks.  count <= 256, world <= 8.
+ *   hw1f_comm_create : allocates this rank's mailbox, returns its 64-byte cudaIpcMemHandle_t
+ *   (exchange the handles with any out-of-band all-gather, e.g. torch.distributed)
+ *   hw1f_comm_connect: maps the peers' mailboxes; all_handles = world * 64 bytes in rank order;
+ *                      cuda_stream = the stream the moments are produced on (engine stream)
+ *   hw1f_comm_allreduce: enqueue; every rank must call it the same number of times
+ *   hw1f_comm_timeouts: number of bounded-spin expiries so far (0 on a healthy run) */
+typedef struct hw1f_comm hw1f_comm;
+int hw1f_comm_create(hw1f_engine* eng, int world, void* ipc_handle64, hw1f_comm** out);
+int hw1f_comm_connect(hw1f_comm* c, int rank, const void* all_handles, void* cuda_stream);
+int hw1f_comm_allreduce(hw1f_comm* c, double* d_data, int32_t count);
+int hw1f_comm_timeouts(hw1f_comm* c, uint32_t* n);
+int hw1f_comm_destroy(hw1f_comm* c);
+const char* hw1f_comm_last_error(const hw1f_comm* c);
+
 /* ---- sample trajectories -------------------------------------------------------------- */
 /* simulate_paths_show<<<1,32>>> (market_data.cuh:136-160; src/1:163): r_paths[n_show*(n_steps+1)].
  * Does NOT advance rng (the reference's write-back is commented out, market_data.cuh:159). */

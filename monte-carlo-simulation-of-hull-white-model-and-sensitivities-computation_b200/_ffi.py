@@ -117,6 +117,12 @@ SYMBOLS = {
                                     C.c_int32, C.POINTER(ZbcResult)]),
     "hw1f_multi_vega_pathwise": (C.c_int, [_P, C.c_uint64, C.c_uint64, C.c_uint64, C.c_float, C.c_float, C.c_float, _P,
                                            _P, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "hw1f_comm_create": (C.c_int, [_P, C.c_int, _P, C.POINTER(_P)]),
+    "hw1f_comm_connect": (C.c_int, [_P, C.c_int, _P, _P]),
+    "hw1f_comm_allreduce": (C.c_int, [_P, _P, C.c_int32]),
+    "hw1f_comm_timeouts": (C.c_int, [_P, C.POINTER(C.c_uint32)]),
+    "hw1f_comm_destroy": (C.c_int, [_P]),
+    "hw1f_comm_last_error": (C.c_char_p, [_P]),
     "hw1f_sample_paths": (C.c_int, [_P, _P, C.c_int32, _P]),
     "hw1f_reduction_bench": (C.c_int, [_P, _P, C.c_int32, C.c_float, C.c_float, C.c_float, _P, _P, C.c_int32,
                                        C.c_int32, C.c_int32, _F, _F]),

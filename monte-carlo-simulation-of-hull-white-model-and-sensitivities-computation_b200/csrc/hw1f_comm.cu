@@ -1,0 +1,178 @@
+// hw1f_comm.cu -- the path's single exchange step as an own kernel over NVLink peer memory.
+//
+// One process per GPU (torchrun).  Every rank owns a small mailbox in device memory that all peers
+// map through CUDA IPC.  hw1f_comm_allreduce enqueues ONE kernel on the engine's stream that
+//   1. posts this rank's moment vector (<= 256 doubles) into its slot of EVERY peer's mailbox
+//      (plain stores over NVLink / NVSwitch), fences at system scope and raises a per-slot flag;
+//   2. waits until all peers' flags for this epoch have arrived in the local mailbox (bounded spin:
+//      a lost peer sets an error flag instead of hanging the GPU);
+//   3. sums the slots in RANK ORDER, so the result is bit-identical on every rank and from run to run
+//      (NCCL's ring/tree order depends on the communicator).
+// Mailboxes are double-buffered by epoch parity: a rank can only reach epoch e+2 after every peer
+// has posted epoch e+1, i.e. after every peer finished reading epoch e.
+//
+// For a 1.6 KB payload the collective is pure latency; this kernel replaces NCCL's ~25 us
+// all-reduce by one NVLink round trip.  NCCL (torch.distributed) remains the plumbing for the
+// handle exchange and the fallback/verification path in bench.py.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "../../include/hw1f.h"
+
+namespace {
+
+constexpr int kMaxWorld = 8;
+constexpr int kMaxCount = 256;
+constexpr unsigned kSpinLimit = 20000000u;  // a few seconds of polling: far beyond any healthy skew, still finite
+
+struct Mailbox {
+    double slots[2][kMaxWorld][kMaxCount];
+    unsigned flags[2][kMaxWorld];
+    unsigned timeouts;
+};
+
+struct CommDev {
+    Mailbox* peer[kMaxWorld];
+    int rank, world;
+};
+
+__global__ void __launch_bounds__(kMaxCount)
+peer_allreduce_kernel(CommDev c, double* __restrict__ data, int count, unsigned epoch)
+{
+    const int i = threadIdx.x;
+    const int p = epoch & 1u;
+    const double mine = (i < count) ? data[i] : 0.0;
+    // 1. post into every mailbox (including our own)
+    if (i < count)
+        for (int r = 0; r < c.world; ++r) c.peer[r]->slots[p][c.rank][i] = mine;
+    __threadfence_system();
+    __syncthreads();
+    if (i < c.world) {
+        volatile unsigned* f = &c.peer[i]->flags[p][c.rank];
+        *f = epoch;
+    }
+    // 2. wait for every peer's post of this epoch in OUR mailbox
+    Mailbox* me = c.peer[c.rank];
+    if (i < c.world) {
+        volatile unsigned* f = &me->flags[p][i];
+        unsigned spins = 0;
+        while (*f != epoch) {
+            if (++spins > kSpinLimit) { atomicAdd(&me->timeouts, 1u); break; }
+            __nanosleep(128);
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    // 3. rank-ordered sum
+    if (i < count) {
+        double acc = 0.0;
+        for (int r = 0; r < c.world; ++r) acc += *(volatile double*)&me->slots[p][r][i];
+        data[i] = acc;
+    }
+}
+
+}  // namespace
+
+struct hw1f_comm {
+    hw1f_engine* eng = nullptr;
+    int device = 0, rank = -1, world = 0;
+    Mailbox* local = nullptr;
+    CommDev dev{};
+    bool opened[kMaxWorld] = {false};
+    unsigned epoch = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+};
+
+extern "C" {
+
+const char* hw1f_comm_last_error(const hw1f_comm* c) { return c ? c->err.c_str() : "null comm"; }
+
+int hw1f_comm_create(hw1f_engine* eng, int world, void* ipc_handle64, hw1f_comm** out)
+{
+    if (!eng || !ipc_handle64 || !out || world < 1 || world > kMaxWorld) return HW1F_ERR_INVALID;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    hw1f_comm* c = new (std::nothrow) hw1f_comm();
+    if (!c) return HW1F_ERR_INVALID;
+    c->eng = eng;
+    c->world = world;
+    hw1f_engine_device(eng, &c->device);
+    cudaSetDevice(c->device);
+    cudaError_t e = cudaMalloc(&c->local, sizeof(Mailbox));
+    if (e == cudaSuccess) e = cudaMemset(c->local, 0, sizeof(Mailbox));
+    cudaIpcMemHandle_t h;
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, c->local);
+    if (e != cudaSuccess) {
+        std::fprintf(stderr, "hw1f_comm_create: %s\n", cudaGetErrorString(e));
+        if (c->local) cudaFree(c->local);
+        delete c;
+        return HW1F_ERR_CUDA;
+    }
+    memcpy(ipc_handle64, &h, 64);
+    *out = c;
+    return HW1F_OK;
+}
+
+int hw1f_comm_connect(hw1f_comm* c, int rank, const void* all_handles, void* cuda_stream)
+{
+    if (!c || !all_handles || rank < 0 || rank >= c->world) return HW1F_ERR_INVALID;
+    cudaSetDevice(c->device);
+    c->rank = rank;
+    c->stream = (cudaStream_t)cuda_stream;
+    c->dev.rank = rank;
+    c->dev.world = c->world;
+    for (int r = 0; r < c->world; ++r) {
+        if (r == rank) { c->dev.peer[r] = c->local; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const char*)all_handles + 64 * (size_t)r, 64);
+        void* p = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            c->err = std::string("cudaIpcOpenMemHandle(rank ") + std::to_string(r) + "): " + cudaGetErrorString(e);
+            cudaGetLastError();
+            return HW1F_ERR_CUDA;
+        }
+        c->dev.peer[r] = (Mailbox*)p;
+        c->opened[r] = true;
+    }
+    return HW1F_OK;
+}
+
+int hw1f_comm_allreduce(hw1f_comm* c, double* d_data, int32_t count)
+{
+    if (!c || !d_data || c->rank < 0) return HW1F_ERR_INVALID;
+    if (count < 1 || count > kMaxCount) { c->err = "count must be in [1,256]"; return HW1F_ERR_INVALID; }
+    cudaSetDevice(c->device);
+    ++c->epoch;
+    peer_allreduce_kernel<<<1, kMaxCount, 0, c->stream>>>(c->dev, d_data, count, c->epoch);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { c->err = std::string("peer_allreduce_kernel: ") + cudaGetErrorString(e); return HW1F_ERR_CUDA; }
+    return HW1F_OK;
+}
+
+int hw1f_comm_timeouts(hw1f_comm* c, uint32_t* n)
+{
+    if (!c || !n) return HW1F_ERR_INVALID;
+    cudaSetDevice(c->device);
+    cudaError_t e = cudaMemcpy(n, &c->local->timeouts, sizeof(unsigned), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) { c->err = cudaGetErrorString(e); return HW1F_ERR_CUDA; }
+    return HW1F_OK;
+}
+
+int hw1f_comm_destroy(hw1f_comm* c)
+{
+    if (!c) return HW1F_OK;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    for (int r = 0; r < c->world; ++r)
+        if (c->opened[r]) cudaIpcCloseMemHandle(c->dev.peer[r]);
+    if (c->local) cudaFree(c->local);
+    delete c;
+    return HW1F_OK;
+}
+
+}  // extern "C"

@@ -40,3 +40,53 @@ def sharded_bond_curve(engine, rng_factory, n_total, device=None):
     engine.bond_curve_moments(rng_factory(first, n), moments.data_ptr())
     allreduce_moments(moments)
     return engine.bond_curve_finish(moments.data_ptr(), n_total)
+
+
+class PeerAllReduce:
+    """hw1f_comm_*: the moment all-reduce as one own kernel over NVLink peer memory (CUDA IPC mailboxes).
+    torch.distributed is only used once, to exchange the 64-byte IPC handles."""
+
+    def __init__(self, engine, stream):
+        import ctypes as C
+        from . import _ffi
+        if not (dist.is_available() and dist.is_initialized()):
+            raise RuntimeError("PeerAllReduce needs an initialised process group")
+        self._C, self._lib = C, _ffi.load()
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        handle = (C.c_ubyte * 64)()
+        h = C.c_void_p()
+        st = self._lib.hw1f_comm_create(engine._h, self.world, handle, C.byref(h))
+        if st != _ffi.OK:
+            raise RuntimeError(f"hw1f_comm_create failed with status {st}")
+        self._h = h
+        mine = torch.tensor(list(bytes(handle)), dtype=torch.uint8, device="cuda")
+        allh = torch.empty(64 * self.world, dtype=torch.uint8, device="cuda")
+        dist.all_gather_into_tensor(allh, mine)
+        blob = bytes(allh.cpu().tolist())
+        buf = (C.c_ubyte * len(blob)).from_buffer_copy(blob)
+        st = self._lib.hw1f_comm_connect(self._h, self.rank, buf, C.c_void_p(stream.cuda_stream))
+        if st != _ffi.OK:
+            msg = self._lib.hw1f_comm_last_error(self._h).decode()
+            self._lib.hw1f_comm_destroy(self._h)
+            self._h = None
+            raise RuntimeError("hw1f_comm_connect: " + msg)
+        dist.barrier()
+
+    def all_reduce(self, moments):
+        """in-place rank-ordered SUM of a float64 CUDA tensor with <= 256 elements (async, stream ordered)"""
+        if moments.dtype != torch.float64 or moments.numel() > 256:
+            raise TypeError("float64 tensor with at most 256 elements")
+        st = self._lib.hw1f_comm_allreduce(self._h, self._C.c_void_p(moments.data_ptr()), moments.numel())
+        if st != 0:
+            raise RuntimeError(self._lib.hw1f_comm_last_error(self._h).decode())
+        return moments
+
+    def timeouts(self):
+        n = self._C.c_uint32()
+        self._lib.hw1f_comm_timeouts(self._h, self._C.byref(n))
+        return n.value
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.hw1f_comm_destroy(self._h)
+            self._h = None

@@ -54,3 +54,19 @@ def test_multi_zbc_and_vega_equal_single_gpu(multi, engine, hw):
     onev = engine.vega_pathwise(hw.Rng(78, n), Pm, fm, n_steps_S1=500)
     assert v.value == pytest.approx(onev["vega_pathwise_f64"], rel=1e-12)
     assert se.value == pytest.approx(onev["vega_pathwise_se"], rel=1e-9)
+
+
+def test_peer_allreduce_kernel_vs_nccl():
+    """own NVLink peer-memory all-reduce (hw1f_comm_*) against NCCL, two ranks under torchrun"""
+    import os
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs at least 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29533",
+                          os.path.join(root, "tools", "peer_allreduce_check.py")],
+                         capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-3000:]
+    assert "peer all-reduce ok on 2 GPUs" in res.stdout
