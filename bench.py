@@ -397,8 +397,9 @@ def main():
                                f"paths x {n_steps} steps per GPU, r0=0.012 a=1 sigma=0.1, {n_mat} maturities, "
                                "seeding included", "arithmetic": args.mode,
                    "paths_per_gpu": 2 * n_paths, "n_steps": n_steps, "l2": "flushed between steps (256 MiB memset, "
-                   "outside the per-step event pairs)", "parallelism": f"path-range sharding x{world}, one NCCL "
-                   "all-reduce of 202 doubles per step" if world > 1 else "single GPU"},
+                   "outside the per-step event pairs)", "parallelism": (f"path-range sharding x{world}, one all-reduce of 202 doubles per step "
+                                                           f"({collective})") if world > 1 else "single GPU"},
+        "collective": {"kind": collective, "check": collective_check},
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": 2 * (n_steps + 2) * 8 + n_mat * 4, "d2h_bytes_per_step": 3 * n_mat * 4},
         "gpu_launches": int(launches),
