@@ -401,7 +401,9 @@ def main():
                                                            f"({collective})") if world > 1 else "single GPU"},
         "collective": {"kind": collective, "check": collective_check},
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms,
-                "h2d_bytes_per_step": 2 * (n_steps + 2) * 8 + n_mat * 4, "d2h_bytes_per_step": 3 * n_mat * 4},
+                # set_model uploads ONE arena: 2 duplicated drift tables + centring + exp(-Im), 256-byte aligned pieces
+                "h2d_bytes_per_step": 2 * (((n_steps + 2) * 8 + 255) // 256 * 256) + 2 * ((n_mat * 4 + 255) // 256 * 256),
+                "d2h_bytes_per_step": 3 * n_mat * 4},
         "gpu_launches": int(launches),
         "clocks": clocks, "clock_check": "rejected: thermal/hw slowdown seen" if bad else "ok",
         "roofline": roofline,

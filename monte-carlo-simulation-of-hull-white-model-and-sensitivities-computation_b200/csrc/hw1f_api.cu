@@ -32,9 +32,11 @@ template <class T>
 struct DevBuf {
     T* p = nullptr;
     size_t cap = 0;   // elements
+    bool view = false;   // non-owning window into the model arena
     cudaError_t ensure(size_t n)
     {
         if (n <= cap) return cudaSuccess;
+        if (view) return cudaErrorInvalidValue;
         if (p) cudaFree(p);
         p = nullptr;
         cap = 0;
@@ -42,7 +44,8 @@ struct DevBuf {
         if (e == cudaSuccess) cap = n;
         return e;
     }
-    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    void set_view(T* ptr, size_t n) { release(); p = ptr; cap = n; view = true; }
+    void release() { if (p && !view) cudaFree(p); p = nullptr; cap = 0; view = false; }
 };
 
 struct Scenario {
@@ -87,6 +90,15 @@ struct hw1f_engine {
     DevBuf<int> d_int;
     void* h_stage = nullptr;             // pinned
     size_t h_stage_bytes = 0;
+    // model arena: base drift, sensitivity drift, centring constants and exp(-Im) in ONE device
+    // allocation with a pinned host mirror, so set_model is a single H2D copy (tables are rebuilt
+    // only when the parameters change)
+    DevBuf<char> d_model;
+    char* h_model = nullptr;
+    size_t model_bytes = 0;
+    bool model_cached = false;
+    hw1f_params cached_p{};
+    cudaEvent_t ev_model = nullptr;
 };
 
 namespace {
@@ -202,15 +214,11 @@ int download(hw1f_engine* e, void* dst, const void* src, size_t bytes)
     return HW1F_OK;
 }
 
-int upload_drift(hw1f_engine* e, int slot, const float* table)
+// noise-free recursion with a drift table (start r0 for rate tables, 0 for the tangent table);
+// fills det_m/det_I[slot] and, for rate tables, emI[n_mat] = exp(-Im) at the save points
+void build_det_tables(hw1f_engine* e, int slot, const float* table, float* emI)
 {
     const int n = e->p.n_steps, nm = e->p.n_mat;
-    HW_CUDA(e, e->d_drift[slot].ensure(n + 2));
-    std::vector<float2> dup(n + 2);
-    for (int i = 0; i < n; ++i) dup[i] = make_float2(table[i], table[i]);
-    dup[n] = dup[n + 1] = make_float2(0.f, 0.f);
-    HW_TRY(upload(e, e->d_drift[slot].p, dup.data(), dup.size() * sizeof(float2)));
-    // noise-free recursion with this table (start r0 for rate tables, 0 for the tangent table)
     std::vector<double>& m = e->det_m[slot];
     std::vector<double>& I = e->det_I[slot];
     m.assign(n + 1, 0.0);
@@ -220,13 +228,25 @@ int upload_drift(hw1f_engine* e, int slot, const float* table)
         m[i + 1] = m[i] * (double)e->exp_adt + (double)table[i];
         I[i + 1] = I[i] + 0.5 * (m[i] + m[i + 1]) * (double)e->dt;
     }
-    if (slot != 1) {
-        std::vector<float> emI(nm, 1.0f);
+    if (emI) {
+        emI[0] = 1.0f;
         for (int k = 1; k < nm; ++k) emI[k] = (float)exp(-I[(size_t)k * e->stride]);
-        HW_CUDA(e, e->d_emI[slot].ensure(nm));
-        HW_TRY(upload(e, e->d_emI[slot].p, emI.data(), emI.size() * sizeof(float)));
     }
-    return HW1F_OK;
+}
+
+// bumped-sigma scenario tables (slots 2, 3): own allocations, uploaded per call
+int upload_drift(hw1f_engine* e, int slot, const float* table)
+{
+    const int n = e->p.n_steps, nm = e->p.n_mat;
+    HW_CUDA(e, e->d_drift[slot].ensure(n + 2));
+    std::vector<float2> dup(n + 2);
+    for (int i = 0; i < n; ++i) dup[i] = make_float2(table[i], table[i]);
+    dup[n] = dup[n + 1] = make_float2(0.f, 0.f);
+    HW_TRY(upload(e, e->d_drift[slot].p, dup.data(), dup.size() * sizeof(float2)));
+    std::vector<float> emI(nm, 1.0f);
+    build_det_tables(e, slot, table, emI.data());
+    HW_CUDA(e, e->d_emI[slot].ensure(nm));
+    return upload(e, e->d_emI[slot].p, emI.data(), emI.size() * sizeof(float));
 }
 
 ModelDev model_dev(const hw1f_engine* e)
@@ -732,7 +752,8 @@ int hw1f_engine_create(int device, hw1f_engine** out)
     e->smem_optin = prop.sharedMemPerBlockOptin;
     if (cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreate(&e->ev0) != cudaSuccess || cudaEventCreate(&e->ev1) != cudaSuccess ||
-        cudaEventCreateWithFlags(&e->ev_stage, cudaEventDisableTiming) != cudaSuccess) {
+        cudaEventCreateWithFlags(&e->ev_stage, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&e->ev_model, cudaEventDisableTiming) != cudaSuccess) {
         delete e;
         return HW1F_ERR_CUDA;
     }
@@ -756,6 +777,9 @@ int hw1f_engine_destroy(hw1f_engine* e)
     e->d_mkt.release(); e->d_center.release(); e->d_plans.release();
     for (auto& d : e->d_emI) d.release(); e->d_partials.release(); e->d_moments.release();
     e->d_out.release(); e->d_int.release();
+    e->d_model.release();
+    if (e->h_model) cudaFreeHost(e->h_model);
+    if (e->ev_model) cudaEventDestroy(e->ev_model);
     if (e->h_stage) cudaFreeHost(e->h_stage);
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
@@ -824,30 +848,62 @@ int hw1f_set_model(hw1f_engine* e, const hw1f_params* p)
     HW_REQUIRE(e, p->n_steps % (p->n_mat - 1) == 0, "N_STEPS must be evenly divisible by (N_MAT - 1)");  // common.cuh:25-27
     HW_REQUIRE(e, p->a > 0.0f && p->sigma > 0.0f && p->T_final > 0.0f, "a, sigma, T_final must be positive");
     HW_CUDA(e, cudaSetDevice(e->device));
-    e->p = *p;
-    e->dt = p->T_final / p->n_steps;                  // H_DT, common.cuh:33
-    e->spacing = p->T_final / (p->n_mat - 1);         // H_MAT_SPACING, common.cuh:34
-    e->exp_adt = expf(-p->a * e->dt);                 // common.cuh:93
-    e->sig_st = host_sig_st(*p, p->sigma);            // common.cuh:94
-    e->stride = p->n_steps / (p->n_mat - 1);          // SAVE_STRIDE, common.cuh:29
-    e->h_drift.assign(p->n_steps, 0.f);
-    e->h_sdrift.assign(p->n_steps, 0.f);
-    host_drift_tables(*p, p->sigma, e->h_drift.data(), e->h_sdrift.data());
-    e->has_model = true;
-    {   // centring constants: c_m = 2 exp(-I_m) along the noise-free path (any value near p0 works)
-        std::vector<float> cen(p->n_mat, 2.0f);
-        double r = p->r0, I = 0.0;
-        for (int i = 1; i <= p->n_steps; ++i) {
-            const double rn = r * (double)e->exp_adt + (double)e->h_drift[i - 1];
-            I += 0.5 * (r + rn) * (double)e->dt;
-            r = rn;
-            if (i % e->stride == 0 && i / e->stride < p->n_mat) cen[i / e->stride] = (float)(2.0 * exp(-I));
+    const int n = p->n_steps, nm = p->n_mat;
+    // arena layout (256-byte aligned pieces): drift2[0], drift2[1], centre[nm], emI[nm]
+    auto align = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t off_d0 = 0, off_d1 = align((size_t)(n + 2) * sizeof(float2));
+    const size_t off_c = off_d1 + align((size_t)(n + 2) * sizeof(float2));
+    const size_t off_e = off_c + align((size_t)nm * sizeof(float));
+    const size_t total = off_e + align((size_t)nm * sizeof(float));
+    const bool same = e->model_cached && memcmp(&e->cached_p, p, sizeof(*p)) == 0 && total == e->model_bytes;
+    if (!same) {
+        // a previous upload may still read the pinned mirror
+        HW_CUDA(e, cudaEventSynchronize(e->ev_model));
+        if (total != e->model_bytes) {
+            HW_CUDA(e, cudaStreamSynchronize(e->stream));
+            e->d_drift[0].release(); e->d_drift[1].release(); e->d_center.release(); e->d_emI[0].release();
+            e->d_model.release();
+            if (e->h_model) cudaFreeHost(e->h_model);
+            e->h_model = nullptr;
+            e->model_bytes = 0;
+            HW_CUDA(e, e->d_model.ensure(total));
+            HW_CUDA(e, cudaMallocHost((void**)&e->h_model, total));
+            e->model_bytes = total;
+            e->d_drift[0].set_view(reinterpret_cast<float2*>(e->d_model.p + off_d0), n + 2);
+            e->d_drift[1].set_view(reinterpret_cast<float2*>(e->d_model.p + off_d1), n + 2);
+            e->d_center.set_view(reinterpret_cast<float*>(e->d_model.p + off_c), nm);
+            e->d_emI[0].set_view(reinterpret_cast<float*>(e->d_model.p + off_e), nm);
         }
-        HW_CUDA(e, e->d_center.ensure(p->n_mat));
-        HW_TRY(upload(e, e->d_center.p, cen.data(), cen.size() * sizeof(float)));
+        e->p = *p;
+        e->dt = p->T_final / p->n_steps;                  // H_DT, common.cuh:33
+        e->spacing = p->T_final / (p->n_mat - 1);         // H_MAT_SPACING, common.cuh:34
+        e->exp_adt = expf(-p->a * e->dt);                 // common.cuh:93
+        e->sig_st = host_sig_st(*p, p->sigma);            // common.cuh:94
+        e->stride = p->n_steps / (p->n_mat - 1);          // SAVE_STRIDE, common.cuh:29
+        e->h_drift.assign(n, 0.f);
+        e->h_sdrift.assign(n, 0.f);
+        host_drift_tables(*p, p->sigma, e->h_drift.data(), e->h_sdrift.data());
+        memset(e->h_model, 0, total);
+        float2* d0 = reinterpret_cast<float2*>(e->h_model + off_d0);
+        float2* d1 = reinterpret_cast<float2*>(e->h_model + off_d1);
+        for (int i = 0; i < n; ++i) {
+            d0[i] = make_float2(e->h_drift[i], e->h_drift[i]);
+            d1[i] = make_float2(e->h_sdrift[i], e->h_sdrift[i]);
+        }
+        float* cen = reinterpret_cast<float*>(e->h_model + off_c);
+        float* emI = reinterpret_cast<float*>(e->h_model + off_e);
+        build_det_tables(e, 0, e->h_drift.data(), emI);
+        build_det_tables(e, 1, e->h_sdrift.data(), nullptr);
+        // centring constants of the reference-order curve kernel: c_m = 2 exp(-I_m) along the noise-free path
+        for (int k = 0; k < nm; ++k) cen[k] = 2.0f * emI[k];
+        e->cached_p = *p;
+        e->model_cached = true;
     }
-    HW_TRY(upload_drift(e, 0, e->h_drift.data()));
-    HW_TRY(upload_drift(e, 1, e->h_sdrift.data()));
+    e->has_model = true;
+    // compute_constants(): ONE host->device copy of the model tables (every call, like the reference's
+    // cudaMemcpyToSymbol sequence; only the host-side table building is cached)
+    HW_CUDA(e, cudaMemcpyAsync(e->d_model.p, e->h_model, total, cudaMemcpyHostToDevice, e->stream));
+    HW_CUDA(e, cudaEventRecord(e->ev_model, e->stream));
     return HW1F_OK;
 }
 
