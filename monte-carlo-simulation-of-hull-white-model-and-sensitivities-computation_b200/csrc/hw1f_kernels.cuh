@@ -19,14 +19,17 @@
 
 namespace hw1f {
 
-constexpr int kThreads = 256;
+#ifndef HW1F_THREADS_LOG2
+#define HW1F_THREADS_LOG2 9            // 512 threads per block, 2 blocks/SM (A/B: profiles/r01_ab_variants_decomposed.txt)
+#endif
+constexpr int kThreads = 1 << HW1F_THREADS_LOG2;
 constexpr int kWarps = kThreads / 32;
 constexpr int kChunk = 2 * kThreads;   // subsequences per block
-constexpr int kChunkLog2 = 9;
+constexpr int kChunkLog2 = HW1F_THREADS_LOG2 + 1;
 constexpr int kMaxRuns = 32;           // seed axis of the batched launches
 constexpr int kMaxScen = 2;            // sigma scenarios sharing one set of normals
 #ifndef HW1F_MIN_BLOCKS
-#define HW1F_MIN_BLOCKS 5              // resident blocks per SM of the single-scenario kernels (48 regs; A/B in profiles/r01_ab_variants.txt)
+#define HW1F_MIN_BLOCKS 2              // resident blocks per SM of the single-scenario kernels (64 regs at 512 threads)
 #endif
 
 struct SeedBlock {
@@ -273,7 +276,7 @@ __device__ __forceinline__ void one_pair(ThreadStreams& t, float2& ns, float2& n
 // vanish in float32 otherwise.  reduce_curve_kernel undoes the centring in double.
 // Blocks stride over chunks; per-warp float trees -> shared floats -> double block accumulators.
 template <int NSCEN>
-__global__ void __launch_bounds__(kThreads, (NSCEN > 1 ? 2 : HW1F_MIN_BLOCKS))
+__global__ void __launch_bounds__(kThreads, (NSCEN > 1 ? 1 : HW1F_MIN_BLOCKS))
 bond_curve_kernel(StreamGeom g, SeedArgs seeds, ModelDev md, ScenDev sc0, ScenDev sc1, double* __restrict__ partials)
 {
     extern __shared__ __align__(16) uint32_t smem[];
@@ -371,7 +374,7 @@ bond_curve_kernel(StreamGeom g, SeedArgs seeds, ModelDev md, ScenDev sc0, ScenDe
 // handles any start parity / step count: `lead` = 1 when the launch starts on the cos half of a
 // Box-Muller pair (odd normal offset), partials[run][block][NSCEN*5] doubles
 template <int NSCEN>
-__global__ void __launch_bounds__(kThreads, (NSCEN > 1 ? 4 : HW1F_MIN_BLOCKS))
+__global__ void __launch_bounds__(kThreads, HW1F_MIN_BLOCKS)
 zbc_kernel(StreamGeom g, SeedArgs seeds, ModelDev md, ScenDev sc0, ScenDev sc1, const BondPlan* __restrict__ plans,
            int n_steps_S1, int lead, float K, double* __restrict__ partials)
 {

@@ -70,7 +70,7 @@ __device__ __forceinline__ void zbc_payoffs(const PairState& st, const BondPlan&
 // METHOD 2: warp shuffle + block shuffle + one atomic per block (simulate_ZBC_warp_optimized, :183-196)
 // METHOD 3: the engine's deterministic tree: no atomics, double partial per block
 template <int METHOD>
-__global__ void __launch_bounds__(kThreads, 4)
+__global__ void __launch_bounds__(kThreads, 2)
 zbc_sum_kernel(StreamGeom g, SeedArgs seeds, ModelDev md, ScenDev sc, const BondPlan* __restrict__ plans,
                int n_steps_S1, int lead, float K, float* __restrict__ sum_f, double* __restrict__ partials)
 {
@@ -151,7 +151,7 @@ constexpr int kFusedFdExtra = 10;  // + 5 ZBC moments at sigma-eps and 5 at sigm
 // FD = true adds the two bumped-sigma antithetic pairs of run_finite_difference (src/3:400-446) on the
 // SAME normals: scm/scp carry sig_st and the shifted drift tables, plans[1], plans[2] their A(S1,S2).
 template <bool FD>
-__global__ void __launch_bounds__(kThreads, (FD ? 2 : 3))
+__global__ void __launch_bounds__(kThreads, 1)
 fused_kernel(StreamGeom g, SeedArgs seeds, ModelDev md, ScenDev sc, ScenDev scm, ScenDev scp,
              const BondPlan* __restrict__ plans, int n_steps_S1, float K, double* __restrict__ partials)
 {

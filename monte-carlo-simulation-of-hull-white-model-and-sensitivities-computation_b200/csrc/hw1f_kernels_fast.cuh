@@ -49,9 +49,9 @@ __device__ __forceinline__ constexpr int ext_pw() { return NZBC > 0 ? 5 : 0; }
 
 template <int NCUR, int NZBC, int PW>
 #ifndef HW1F_FAST_MIN_BLOCKS
-#define HW1F_FAST_MIN_BLOCKS 4   // A/B in profiles/r01_ab_variants_decomposed.txt: 4 blocks (64 regs) beats 5..8
+#define HW1F_FAST_MIN_BLOCKS 2   // A/B in profiles/r01_ab_variants_decomposed.txt: 512 threads x 2 blocks (64 regs) is best
 #endif
-__global__ void __launch_bounds__(kThreads, (NZBC + PW >= 3 ? 3 : HW1F_FAST_MIN_BLOCKS))
+__global__ void __launch_bounds__(kThreads, HW1F_FAST_MIN_BLOCKS)
 fast_kernel(StreamGeom g, SeedArgs seeds, ModelDev md, FastScen cs0, FastScen cs1, FastScen zs0, FastScen zs1,
             FastScen zs2, FastTangent tg, const BondPlan* __restrict__ plans, int n_steps_S1, int lead, float K,
             double* __restrict__ partials)

@@ -305,3 +305,15 @@ def test_other_model_parameters(hw, over, mode):
         assert v["vega_pathwise_f64"] == pytest.approx(s / n, rel=2e-5, abs=1e-7)
     finally:
         eng.close()
+
+
+def test_far_subsequences_and_offsets(engine, hw, oracle, curve):
+    """path ranges far from 0 (hi part of the jump tables) and large normal offsets (T^offset folded on the host)"""
+    first, n = (1 << 33) + 12345, 3000
+    c = engine.bond_curve(hw.Rng(SEED, n, first_path=first).seek(100000))
+    s, _ = oracle.bond_curve_sums(SEED, n, first_path=first, offset=100000)
+    P, f = oracle.curve_finalize(s, n)
+    assert np.abs(c["P"] / P - 1).max() < 1e-6 and np.abs(c["f"] - f).max() < 5e-6
+    z = engine.zbc_cv(hw.Rng(SEED, n, first_path=first).seek(1000001), curve["P"], curve["f"], n_steps_S1=499)
+    mom = oracle.zbc_moments(SEED, n, curve["P"], curve["f"], n_steps_S1=499, first_path=first, offset=1000001)
+    assert np.allclose(z["mom"], mom, rtol=5e-6)
