@@ -80,7 +80,7 @@ int main()
 
     std::printf("\n");
     if (ask_yes("Run block size optimization sweep? (y/n): "))
-        std::printf("\nThe B200 engine uses one fixed launch shape (256 threads, 2 subsequences per thread, 4 blocks/SM);\n"
+        std::printf("\nThe B200 engine uses one fixed launch shape (512 threads, 2 subsequences per thread, 2 blocks/SM);\n"
                     "the reference's block-size sweep tunes its own kernel and has no counterpart here.\n");
 
     std::printf("\nFINITE DIFFERENCE APPROXIMATION\n\n");

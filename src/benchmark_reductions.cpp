@@ -22,7 +22,7 @@ int main()
     const float S1 = 5.0f, S2 = 10.0f, K = std::exp(-0.1f);
     std::printf("Test Parameters:\n  Option: ZBC(S1=%.1f, S2=%.1f, K=%.6f)\n  Paths: %llu (x2 antithetic = %llu effective)\n", S1, S2, K,
                 (unsigned long long)kNPaths, (unsigned long long)(2 * kNPaths));
-    std::printf("  Block config: 256 threads/block, 2 subsequences per thread\n  Number of benchmark runs: 5 (average taken)\n\nRunning benchmarks...\n\n");
+    std::printf("  Block config: 512 threads/block, 2 subsequences per thread\n  Number of benchmark runs: 5 (average taken)\n\nRunning benchmarks...\n\n");
 
     const char* names[4] = {"Naive (direct atomicAdd)", "Shared Memory Reduction", "Warp+Block Optimized", "Deterministic two-level tree"};
     Rng rng(base_time(), kNPaths);   // one stream set shared by all methods, advanced by every launch
@@ -44,7 +44,7 @@ int main()
 
     if (FILE* js = std::fopen("data/benchmark_reductions.json", "w")) {
         std::fprintf(js, "{\n  \"benchmark\": \"Reduction Methods Performance\",\n  \"parameters\": {\n    \"N_PATHS\": %llu,\n    \"NTPB\": %d,\n    \"NB\": %llu,\n",
-                     (unsigned long long)kNPaths, 256, (unsigned long long)(kNPaths / 512));
+                     (unsigned long long)kNPaths, 512, (unsigned long long)(kNPaths / 1024));
         std::fprintf(js, "    \"S1\": %.1f,\n    \"S2\": %.1f,\n    \"K\": %.6f\n  },\n  \"results\": [\n", S1, S2, K);
         for (size_t i = 0; i < rows.size(); ++i)
             std::fprintf(js, "    {\n      \"method\": \"%s\",\n      \"time_ms\": %.3f,\n      \"throughput_Mpaths_per_sec\": %.2f,\n      \"price\": %.8f\n    }%s\n",
