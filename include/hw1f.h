@@ -236,6 +236,16 @@ int hw1f_fused(hw1f_engine* eng, hw1f_rng* rng, float S1, float S2, float K,
                float* P, float* f, float* P_se, hw1f_zbc_result* zbc, hw1f_vega_result* vega,
                float* sim_ms);
 
+/* finalisation of a fused moment vector (after an optional all-reduce across ranks): the curve epilogue,
+ * the ZBC algebra and the vegas from d_moments[2*n_mat + HW1F_FUSED_EXTRA (+ HW1F_FUSED_FD_EXTRA)].
+ * eps > 0: the vector carries the FD block (hw1f_fused_fd_moments) and vega->price_minus/plus/vega_fd are
+ * filled; eps <= 0: hw1f_fused_moments layout.  P0S2 = P_mkt[n_mat-1] of the market curve the pass used.
+ * n_paths_total may exceed the reference's `int N_total` range (up to 2^40 subsequences: the scaling run);
+ * the float32 algebra of src/2:154-179 then simply continues with (float)N_total. */
+int hw1f_fused_finish(hw1f_engine* eng, const double* d_moments, uint64_t n_paths_total, float P0S2, float eps,
+                      int32_t n_steps_S1, float* P, float* f, float* P_se, hw1f_zbc_result* zbc,
+                      hw1f_vega_result* vega);
+
 /* ---- single-process multi-GPU front end ------------------------------------------------------ */
 /* One engine per device, paths sharded by contiguous XORWOW subsequence range (the union equals the
  * single-GPU path set bit for bit), ONE ncclAllReduce(ncclDouble, ncclSum) of the packed moment vector
@@ -254,6 +264,12 @@ int hw1f_multi_bond_curve(hw1f_multi* m, uint64_t seed, uint64_t n_paths_total, 
 int hw1f_multi_zbc_cv(hw1f_multi* m, uint64_t seed, uint64_t n_paths_total, uint64_t normal_offset,
                       float S1, float S2, float K, const float* P_mkt, const float* f_mkt,
                       int32_t n_steps_S1, hw1f_zbc_result* out);
+/* the BASELINE.json scaling run: hw1f_fused_fd_moments on every device's shard, one all-reduce of
+ * 2*n_mat + 18 doubles, hw1f_fused_finish on device 0.  wall_ms: CUDA-event time on device 0 from the first
+ * launch to the end of the all-reduce (may be NULL). */
+int hw1f_multi_fused(hw1f_multi* m, uint64_t seed, uint64_t n_paths_total, uint64_t normal_offset, float S1, float S2,
+                     float K, const float* P_mkt, const float* f_mkt, float eps, int32_t n_steps_S1, float* P,
+                     float* f, float* P_se, hw1f_zbc_result* zbc, hw1f_vega_result* vega, float* wall_ms);
 int hw1f_multi_vega_pathwise(hw1f_multi* m, uint64_t seed, uint64_t n_paths_total, uint64_t normal_offset,
                              float S1, float S2, float K, const float* P_mkt, const float* f_mkt,
                              int32_t n_steps_S1, double* vega, double* vega_se);

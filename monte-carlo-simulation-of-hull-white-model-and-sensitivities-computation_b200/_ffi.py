@@ -106,6 +106,8 @@ SYMBOLS = {
     "hw1f_fused_fd_moments": (C.c_int, [_P, _P, C.c_float, C.c_float, C.c_float, _P, _P, C.c_float, C.c_int32, _P]),
     "hw1f_fused": (C.c_int, [_P, _P, C.c_float, C.c_float, C.c_float, _P, _P, C.c_float, C.c_int32, _P, _P, _P,
                              C.POINTER(ZbcResult), C.POINTER(VegaResult), _F]),
+    "hw1f_fused_finish": (C.c_int, [_P, _P, C.c_uint64, C.c_float, C.c_float, C.c_int32, _P, _P, _P,
+                                    C.POINTER(ZbcResult), C.POINTER(VegaResult)]),
     "hw1f_multi_create": (C.c_int, [C.c_int, C.POINTER(_P)]),
     "hw1f_multi_destroy": (C.c_int, [_P]),
     "hw1f_multi_device_count": (C.c_int, [_P, C.POINTER(C.c_int)]),
@@ -115,6 +117,8 @@ SYMBOLS = {
     "hw1f_multi_bond_curve": (C.c_int, [_P, C.c_uint64, C.c_uint64, C.c_uint64, _P, _P, _P, _F]),
     "hw1f_multi_zbc_cv": (C.c_int, [_P, C.c_uint64, C.c_uint64, C.c_uint64, C.c_float, C.c_float, C.c_float, _P, _P,
                                     C.c_int32, C.POINTER(ZbcResult)]),
+    "hw1f_multi_fused": (C.c_int, [_P, C.c_uint64, C.c_uint64, C.c_uint64, C.c_float, C.c_float, C.c_float, _P, _P,
+                                   C.c_float, C.c_int32, _P, _P, _P, C.POINTER(ZbcResult), C.POINTER(VegaResult), _F]),
     "hw1f_multi_vega_pathwise": (C.c_int, [_P, C.c_uint64, C.c_uint64, C.c_uint64, C.c_float, C.c_float, C.c_float, _P,
                                            _P, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "hw1f_comm_create": (C.c_int, [_P, C.c_int, _P, C.POINTER(_P)]),

@@ -598,7 +598,9 @@ void zbc_algebra(const double mom[5], uint64_t n_paths_total, float P0S2, int32_
 {
     memset(r, 0, sizeof(*r));
     for (int k = 0; k < 5; ++k) r->mom[k] = mom[k];
-    const int N_total = (int)(2 * n_paths_total);
+    // the reference divides by `int N_total` (src/2:154): the same value as a float for every count an int
+    // can hold; beyond 2^31 - 1 (multi-GPU scaling run) the float algebra simply continues with (float)N
+    const float N_total = (float)(2 * n_paths_total);
     r->n_total = 2 * n_paths_total;
     r->n_steps_S1 = n_steps_S1;
     const float h_ZBC = (float)mom[0], h_control = (float)mom[1], h_ZBC_sq = (float)mom[2],
@@ -1013,7 +1015,7 @@ int hw1f_bond_curve_finish(hw1f_engine* e, const double* d_moments, uint64_t n_p
 {
     HW_TRY(require_model(e));
     if (!d_moments || !P || !f) return HW1F_ERR_INVALID;
-    HW_REQUIRE(e, 2 * n_paths_total < (1ull << 31), "the reference's (float)n_paths epilogue needs 2*n_paths < 2^31");
+    HW_REQUIRE(e, n_paths_total >= 1 && n_paths_total < (1ull << 40), "n_paths_total outside [1, 2^40)");
     HW_CUDA(e, cudaSetDevice(e->device));
     const int n = e->p.n_mat;
     HW_CUDA(e, e->d_out.ensure(4 * (size_t)n));
@@ -1093,7 +1095,7 @@ int hw1f_zbc_cv_finish(hw1f_engine* e, const double* d_moments, uint64_t n_paths
 {
     HW_TRY(require_model(e));
     if (!d_moments || !out) return HW1F_ERR_INVALID;
-    HW_REQUIRE(e, 2 * n_paths_total < (1ull << 31), "the reference's int N_total needs 2*n_paths < 2^31");
+    HW_REQUIRE(e, n_paths_total >= 1 && n_paths_total < (1ull << 40), "n_paths_total outside [1, 2^40)");
     HW_CUDA(e, cudaSetDevice(e->device));
     double mom[5];
     HW_TRY(download(e, mom, d_moments, sizeof(mom)));
@@ -1441,38 +1443,51 @@ int hw1f_fused_fd_moments(hw1f_engine* e, hw1f_rng* rng, float S1, float S2, flo
     return fused_launch(e, rng, S1, S2, K, P_mkt, f_mkt, true, eps, n_steps_S1, d_moments);
 }
 
-int hw1f_fused(hw1f_engine* e, hw1f_rng* rng, float S1, float S2, float K, const float* P_mkt, const float* f_mkt,
-               float eps, int32_t n_steps_S1, float* P, float* f, float* P_se, hw1f_zbc_result* zbc,
-               hw1f_vega_result* vega, float* sim_ms)
+int hw1f_fused_finish(hw1f_engine* e, const double* d_moments, uint64_t n_paths_total, float P0S2, float eps,
+                      int32_t n_steps_S1, float* P, float* f, float* P_se, hw1f_zbc_result* zbc, hw1f_vega_result* vega)
 {
     HW_TRY(require_model(e));
-    if (!rng || !P || !f || !zbc || !vega) return HW1F_ERR_INVALID;
-    HW_REQUIRE(e, 2 * rng->n_paths < (1ull << 31), "the reference's int N_total needs 2*n_paths < 2^31");
+    if (!d_moments || !P || !f || !zbc || !vega) return HW1F_ERR_INVALID;
     HW_CUDA(e, cudaSetDevice(e->device));
-    int32_t n = 0;
-    HW_TRY(resolve_steps(e, S1, n_steps_S1, &n));
-    const int nm = e->p.n_mat, next = kFusedExtra + kFusedFdExtra;
-    HW_CUDA(e, e->d_moments.ensure(4 * (size_t)nm * kMaxRuns));
-    HW_TRY(warm_geometry(e, rng));
-    HW_CUDA(e, cudaEventRecord(e->ev0, e->stream));
-    HW_TRY(fused_launch(e, rng, S1, S2, K, P_mkt, f_mkt, true, eps, n, e->d_moments.p));
-    HW_CUDA(e, cudaEventRecord(e->ev1, e->stream));
-    HW_TRY(hw1f_bond_curve_finish(e, e->d_moments.p, rng->n_paths, P, f, P_se));
+    const bool fd = eps > 0.0f;
+    const int nm = e->p.n_mat, next = kFusedExtra + (fd ? kFusedFdExtra : 0);
+    HW_TRY(hw1f_bond_curve_finish(e, d_moments, n_paths_total, P, f, P_se));
     std::vector<double> ext(next);
-    HW_TRY(download(e, ext.data(), e->d_moments.p + 2 * nm, ext.size() * sizeof(double)));
-    const float P0S2 = P_mkt[nm - 1];
-    zbc_algebra(ext.data(), rng->n_paths, P0S2, n, zbc);
+    HW_TRY(download(e, ext.data(), d_moments + 2 * nm, ext.size() * sizeof(double)));
+    zbc_algebra(ext.data(), n_paths_total, P0S2, n_steps_S1, zbc);
     memset(vega, 0, sizeof(*vega));
-    vega->n_steps_S1 = n;
-    const double np2 = 2.0 * (double)rng->n_paths, np1 = (double)rng->n_paths;
+    vega->n_steps_S1 = n_steps_S1;
+    const double np2 = 2.0 * (double)n_paths_total, np1 = (double)n_paths_total;
     vega->vega_pathwise_f64 = ext[5] / np2;                 // both antithetic twins
     vega->vega_pathwise = (float)vega->vega_pathwise_f64;
     const double mean_pair = ext[5] / np1;                  // pair sums: var of the pair mean
     const double var_pair = (np1 > 1) ? (ext[6] - np1 * mean_pair * mean_pair) / (np1 - 1.0) : 0.0;
     vega->vega_pathwise_se = (var_pair > 0) ? 0.5 * sqrt(var_pair / np1) : 0.0;
-    vega->price_minus = zbc_price_cv(ext.data() + kFusedExtra, rng->n_paths, P0S2);
-    vega->price_plus = zbc_price_cv(ext.data() + kFusedExtra + 5, rng->n_paths, P0S2);
-    vega->vega_fd = (vega->price_plus - vega->price_minus) / (2.0f * eps);
+    if (fd) {
+        vega->price_minus = zbc_price_cv(ext.data() + kFusedExtra, n_paths_total, P0S2);
+        vega->price_plus = zbc_price_cv(ext.data() + kFusedExtra + 5, n_paths_total, P0S2);
+        vega->vega_fd = (vega->price_plus - vega->price_minus) / (2.0f * eps);
+    }
+    return HW1F_OK;
+}
+
+int hw1f_fused(hw1f_engine* e, hw1f_rng* rng, float S1, float S2, float K, const float* P_mkt, const float* f_mkt,
+               float eps, int32_t n_steps_S1, float* P, float* f, float* P_se, hw1f_zbc_result* zbc,
+               hw1f_vega_result* vega, float* sim_ms)
+{
+    HW_TRY(require_model(e));
+    if (!rng || !P_mkt || !f_mkt || !P || !f || !zbc || !vega) return HW1F_ERR_INVALID;
+    HW_REQUIRE(e, eps > 0.0f, "hw1f_fused needs eps > 0 (the FD bumps ride on the same launch)");
+    HW_CUDA(e, cudaSetDevice(e->device));
+    int32_t n = 0;
+    HW_TRY(resolve_steps(e, S1, n_steps_S1, &n));
+    const int nm = e->p.n_mat;
+    HW_CUDA(e, e->d_moments.ensure(4 * (size_t)nm * kMaxRuns));
+    HW_TRY(warm_geometry(e, rng));
+    HW_CUDA(e, cudaEventRecord(e->ev0, e->stream));
+    HW_TRY(fused_launch(e, rng, S1, S2, K, P_mkt, f_mkt, true, eps, n, e->d_moments.p));
+    HW_CUDA(e, cudaEventRecord(e->ev1, e->stream));
+    HW_TRY(hw1f_fused_finish(e, e->d_moments.p, rng->n_paths, P_mkt[nm - 1], eps, n, P, f, P_se, zbc, vega));
     float ms = 0.f;
     HW_CUDA(e, cudaEventElapsedTime(&ms, e->ev0, e->ev1));
     vega->ms_pathwise = vega->ms_fd = ms;

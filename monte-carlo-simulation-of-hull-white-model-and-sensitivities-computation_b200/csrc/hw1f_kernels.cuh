@@ -632,7 +632,8 @@ __global__ void curve_epilogue_kernel(const double* __restrict__ moments, int n_
 {
     extern __shared__ float s_P[];
     const int m = threadIdx.x;
-    const float n_paths_f = __int2float_rn((int)(2ull * n_pairs));   // (float)n_paths, int like the reference
+    // (float)n_paths of the reference (an int there); same value from the 64-bit count, and defined beyond 2^31
+    const float n_paths_f = __ull2float_rn(2ull * n_pairs);
     if (m < n_mat) {
         // P_sum[0] = 2.0f * N_PATHS (market_data.cuh:76-78)
         const float sum = (m == 0) ? mul_(2.0f, __ull2float_rn(n_pairs)) : __double2float_rn(moments[m]);

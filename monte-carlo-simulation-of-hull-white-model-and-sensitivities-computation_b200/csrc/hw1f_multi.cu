@@ -257,6 +257,46 @@ int hw1f_multi_zbc_cv(hw1f_multi* m, uint64_t seed, uint64_t n_paths_total, uint
     return HW1F_OK;
 }
 
+int hw1f_multi_fused(hw1f_multi* m, uint64_t seed, uint64_t n_paths_total, uint64_t normal_offset, float S1, float S2,
+                     float K, const float* P_mkt, const float* f_mkt, float eps, int32_t n_steps_S1, float* P,
+                     float* f, float* P_se, hw1f_zbc_result* zbc, hw1f_vega_result* vega, float* wall_ms)
+{
+    if (!m || !P_mkt || !f_mkt || !P || !f || !zbc || !vega) return HW1F_ERR_INVALID;
+    M_REQUIRE(m, m->has_model, "hw1f_multi_set_model() has not been called");
+    M_REQUIRE(m, eps > 0.0f, "hw1f_multi_fused needs eps > 0");
+    const size_t count = 2 * (size_t)m->p.n_mat + HW1F_FUSED_EXTRA + HW1F_FUSED_FD_EXTRA;
+    int s = ensure_moments(m, 4 * (size_t)m->p.n_mat + 64);
+    if (s != HW1F_OK) return s;
+    int32_t n = n_steps_S1;
+    if (n < 0) M_ENG(m, 0, hw1f_steps_to(m->eng[0], S1, &n));
+    Rngs rngs;
+    s = make_rngs(m, seed, n_paths_total, normal_offset, &rngs);
+    if (s != HW1F_OK) return s;
+    for (int d = 0; d < m->n; ++d) M_ENG(m, d, hw1f_rng_prepare(m->eng[d], rngs.h[d]));
+    cudaEvent_t e0, e1;
+    M_CUDA(m, cudaSetDevice(0));
+    M_CUDA(m, cudaEventCreate(&e0));
+    M_CUDA(m, cudaEventCreate(&e1));
+    M_CUDA(m, cudaEventRecord(e0, m->stream[0]));
+    for (int d = 0; d < m->n; ++d)
+        M_ENG(m, d, hw1f_fused_fd_moments(m->eng[d], rngs.h[d], S1, S2, K, P_mkt, f_mkt, eps, n, m->d_mom[d]));
+    s = allreduce(m, count);
+    if (s != HW1F_OK) return s;
+    M_CUDA(m, cudaSetDevice(0));
+    M_CUDA(m, cudaEventRecord(e1, m->stream[0]));
+    M_ENG(m, 0, hw1f_fused_finish(m->eng[0], m->d_mom[0], n_paths_total, P_mkt[m->p.n_mat - 1], eps, n, P, f, P_se, zbc,
+                                  vega));
+    for (int d = 1; d < m->n; ++d) { M_CUDA(m, cudaSetDevice(d)); M_CUDA(m, cudaStreamSynchronize(m->stream[d])); }
+    float ms = 0.f;
+    M_CUDA(m, cudaSetDevice(0));
+    M_CUDA(m, cudaEventElapsedTime(&ms, e0, e1));
+    vega->ms_pathwise = vega->ms_fd = ms;
+    if (wall_ms) *wall_ms = ms;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return HW1F_OK;
+}
+
 int hw1f_multi_vega_pathwise(hw1f_multi* m, uint64_t seed, uint64_t n_paths_total, uint64_t normal_offset, float S1,
                              float S2, float K, const float* P_mkt, const float* f_mkt, int32_t n_steps_S1,
                              double* vega, double* vega_se)

@@ -305,6 +305,15 @@ class Engine:
             self._check(self._lib.hw1f_fused_fd_moments(self._h, rng._h, S1, S2, K, _ptr(P_mkt), _ptr(f_mkt), eps,
                                                         n_steps_S1, C.c_void_p(d_moments_ptr)))
 
+    def fused_finish(self, d_moments_ptr, n_paths_total, P0S2, eps=None, n_steps_S1=0):
+        """finalise a (possibly all-reduced) fused moment vector; eps as passed to fused_moments"""
+        P, f, se = (np.zeros(self.n_mat, np.float32) for _ in range(3))
+        z, v = ZbcResult(), VegaResult()
+        self._check(self._lib.hw1f_fused_finish(self._h, C.c_void_p(d_moments_ptr), n_paths_total, P0S2,
+                                                0.0 if eps is None else eps, n_steps_S1, _ptr(P), _ptr(f), _ptr(se),
+                                                C.byref(z), C.byref(v)))
+        return {"P": P, "f": f, "P_se": se, "zbc": z.as_dict(), "vega": v.as_dict()}
+
     # -- simulate_paths_show (src/1:156-171) --
     def sample_paths(self, rng, n_show=32):
         out = np.zeros((n_show, self.n_steps + 1), np.float32)

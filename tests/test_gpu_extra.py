@@ -174,6 +174,56 @@ def test_fused_with_fd_bumps_one_launch(engine, hw, curve):
     assert 0 < got["vega"]["vega_pathwise_se"] < pw["vega_pathwise_se"]      # antithetic twins: smaller error
 
 
+def test_fused_shards_allreduce_finish(engine, hw, curve):
+    """the scaling-run shape on one GPU: two disjoint subsequence shards -> hw1f_fused_fd_moments each -> sum of
+    the moment vectors (what the all-reduce does) -> hw1f_fused_finish == hw1f_fused over the whole range"""
+    import torch
+    nm = engine.n_mat
+    whole = engine.fused(hw.Rng(SEED, N), curve["P"], curve["f"], eps=0.001, n_steps_S1=500)
+    acc = torch.zeros(2 * nm + 18, dtype=torch.float64, device="cuda")
+    part = torch.zeros_like(acc)
+    torch.cuda.synchronize()
+    cut = 5555                                             # ragged split: neither shard is chunk aligned
+    for first, cnt in ((0, cut), (cut, N - cut)):
+        engine.fused_moments(hw.Rng(SEED, cnt, first_path=first), curve["P"], curve["f"], part.data_ptr(), eps=0.001,
+                             n_steps_S1=500)
+        engine.synchronize()
+        acc += part
+    torch.cuda.synchronize()
+    got = engine.fused_finish(acc.data_ptr(), N, float(curve["P"][-1]), eps=0.001, n_steps_S1=500)
+    assert np.abs(got["P"] / whole["P"] - 1).max() < 2e-7 and np.abs(got["f"] - whole["f"]).max() < 2e-6
+    assert np.allclose(got["zbc"]["mom"], whole["zbc"]["mom"], rtol=1e-12)
+    assert got["zbc"]["price_cv"] == pytest.approx(whole["zbc"]["price_cv"], rel=1e-6)
+    assert got["vega"]["vega_pathwise_f64"] == pytest.approx(whole["vega"]["vega_pathwise_f64"], rel=1e-12)
+    assert got["vega"]["vega_fd"] == pytest.approx(whole["vega"]["vega_fd"], rel=1e-4)
+
+
+def test_finish_beyond_int_range(engine, hw, curve):
+    """2*n_paths >= 2^31 (the 2^30-subsequence scaling run) is outside the reference's `int N_total`; the finish
+    calls must keep working there.  Moments of a 2^14 run scaled by 2^18 stand in for a 2^32-subsequence run:
+    every mean is unchanged, standard errors shrink by sqrt(2^18) = 512."""
+    import torch
+    SCALE = 1 << 18
+    nm = engine.n_mat
+    mom = torch.zeros(2 * nm + 18, dtype=torch.float64, device="cuda")
+    torch.cuda.synchronize()
+    engine.fused_moments(hw.Rng(SEED, N), curve["P"], curve["f"], mom.data_ptr(), eps=0.001, n_steps_S1=500)
+    engine.synchronize()
+    small = engine.fused_finish(mom.data_ptr(), N, float(curve["P"][-1]), eps=0.001, n_steps_S1=500)
+    big_mom = mom * float(SCALE)
+    torch.cuda.synchronize()
+    big = engine.fused_finish(big_mom.data_ptr(), N * SCALE, float(curve["P"][-1]), eps=0.001, n_steps_S1=500)
+    assert big["zbc"]["n_total"] == 2 * N * SCALE and big["zbc"]["n_total"] >= 1 << 31
+    assert np.abs(big["P"] / small["P"] - 1).max() < 2e-7 and np.abs(big["f"] - small["f"]).max() < 2e-6
+    assert big["zbc"]["price_cv"] == pytest.approx(small["zbc"]["price_cv"], rel=1e-6)
+    assert big["zbc"]["beta"] == pytest.approx(small["zbc"]["beta"], rel=1e-5)
+    assert big["vega"]["vega_pathwise_f64"] == pytest.approx(small["vega"]["vega_pathwise_f64"], rel=1e-12)
+    assert big["vega"]["vega_pathwise_se"] == pytest.approx(small["vega"]["vega_pathwise_se"] / SCALE ** 0.5, rel=1e-3)
+    assert big["P_se"][50] == pytest.approx(small["P_se"][50] / SCALE ** 0.5, rel=1e-3)
+    z = engine.zbc_cv_finish(big_mom.data_ptr() + 8 * 2 * nm, N * SCALE, float(curve["P"][-1]))
+    assert z["price_cv"] == big["zbc"]["price_cv"]
+
+
 def test_engine_lifecycle_and_argument_errors(hw, curve):
     """create/destroy repeatedly, bad arguments come back as status codes, never as a crash or exit()"""
     import ctypes as C

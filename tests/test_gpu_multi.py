@@ -56,6 +56,27 @@ def test_multi_zbc_and_vega_equal_single_gpu(multi, engine, hw):
     assert se.value == pytest.approx(onev["vega_pathwise_se"], rel=1e-9)
 
 
+def test_multi_fused_equals_single_gpu(multi, engine, hw):
+    """the scaling-run call: fused pass sharded over two devices, one all-reduce, finish on device 0"""
+    lib, h = multi
+    n = (1 << 20) + 5
+    c = engine.bond_curve(hw.Rng(1, 1 << 20))
+    Pm, fm = np.ascontiguousarray(c["P"]), np.ascontiguousarray(c["f"])
+    P, f, se = (np.zeros(101, np.float32) for _ in range(3))
+    z, v, ms = hw.package.ZbcResult(), hw.package.VegaResult(), C.c_float()
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    st = lib.hw1f_multi_fused(h, 4321, n, 0, 5.0, 10.0, engine.K_DEFAULT, vp(Pm), vp(fm), 0.001, 500, vp(P), vp(f),
+                              vp(se), C.byref(z), C.byref(v), C.byref(ms))
+    assert st == 0, lib.hw1f_multi_last_error(h)
+    one = engine.fused(hw.Rng(4321, n), Pm, fm, eps=0.001, n_steps_S1=500)
+    assert np.abs(P / one["P"] - 1).max() < 2e-7 and np.abs(f - one["f"]).max() < 2e-6
+    assert np.allclose(list(z.mom), one["zbc"]["mom"], rtol=1e-12)
+    assert z.price_cv == pytest.approx(one["zbc"]["price_cv"], rel=1e-6)
+    assert v.vega_pathwise_f64 == pytest.approx(one["vega"]["vega_pathwise_f64"], rel=1e-12)
+    assert v.vega_fd == pytest.approx(one["vega"]["vega_fd"], rel=1e-4)
+    assert ms.value > 0
+
+
 def test_peer_allreduce_kernel_vs_nccl():
     """own NVLink peer-memory all-reduce (hw1f_comm_*) against NCCL, two ranks under torchrun"""
     import os
