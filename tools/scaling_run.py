@@ -26,6 +26,10 @@ CLOSED_FORM = {"P_0_5": 0.947126, "P_0_10": 0.859387, "zbc": 0.025255}
 
 
 def main():
+    # stdout carries exactly one JSON line (rank 0); library banners (NCCL) go to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--total-log2", type=int, default=30, help="total XORWOW subsequences over all ranks")
     ap.add_argument("--collective", default="peer", choices=["peer", "nccl"])
@@ -111,7 +115,7 @@ def main():
                                 "P_0_10": float(res["P"][100]) - CLOSED_FORM["P_0_10"],
                                 "zbc": z["price_cv_f64"] - CLOSED_FORM["zbc"]},
     }
-    print(json.dumps(line))
+    os.write(real_stdout, (json.dumps(line) + "\n").encode())
 
 
 if __name__ == "__main__":
