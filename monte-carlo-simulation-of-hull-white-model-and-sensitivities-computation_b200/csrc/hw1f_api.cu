@@ -99,6 +99,19 @@ struct hw1f_engine {
     bool model_cached = false;
     hw1f_params cached_p{};
     cudaEvent_t ev_model = nullptr;
+    // FD arena: shifted drift tables and exp(-Im) of the sigma -/+ eps scenarios (slots 2, 3) in one device
+    // allocation with a pinned host mirror; rebuilt on the host only when (model, sigma pair) changes,
+    // uploaded with ONE copy per pricing call (the reference re-sends the tables per bump, src/3:416-441)
+    DevBuf<char> d_fd;
+    char* h_fd = nullptr;
+    size_t fd_bytes = 0;
+    bool fd_cached = false;
+    float fd_sig[2] = {0.f, 0.f};
+    cudaEvent_t ev_fd = nullptr;
+    // (int)(S1/d_dt) as the device evaluates it (hw1f_steps_to): one probe per (S1, dt)
+    bool steps_cached = false;
+    float steps_S1 = 0.f, steps_dt = 0.f;
+    int32_t steps_n = 0;
 };
 
 namespace {
@@ -234,19 +247,48 @@ void build_det_tables(hw1f_engine* e, int slot, const float* table, float* emI)
     }
 }
 
-// bumped-sigma scenario tables (slots 2, 3): own allocations, uploaded per call
-int upload_drift(hw1f_engine* e, int slot, const float* table)
+// bumped-sigma scenario tables (slots 2, 3) of run_finite_difference (src/3:400-446): shifted drift tables
+// (duplicated float2) and exp(-Im) of sigma -/+ eps.  Host-side construction is cached per (model, sigma
+// pair); every call sends the arena with one stream-ordered copy.
+int upload_fd_tables(hw1f_engine* e, float sig_m, float sig_p)
 {
     const int n = e->p.n_steps, nm = e->p.n_mat;
-    HW_CUDA(e, e->d_drift[slot].ensure(n + 2));
-    std::vector<float2> dup(n + 2);
-    for (int i = 0; i < n; ++i) dup[i] = make_float2(table[i], table[i]);
-    dup[n] = dup[n + 1] = make_float2(0.f, 0.f);
-    HW_TRY(upload(e, e->d_drift[slot].p, dup.data(), dup.size() * sizeof(float2)));
-    std::vector<float> emI(nm, 1.0f);
-    build_det_tables(e, slot, table, emI.data());
-    HW_CUDA(e, e->d_emI[slot].ensure(nm));
-    return upload(e, e->d_emI[slot].p, emI.data(), emI.size() * sizeof(float));
+    auto align = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t sz_d = align((size_t)(n + 2) * sizeof(float2)), sz_e = align((size_t)nm * sizeof(float));
+    const size_t total = 2 * sz_d + 2 * sz_e;
+    if (total != e->fd_bytes) {
+        HW_CUDA(e, cudaStreamSynchronize(e->stream));
+        e->d_drift[2].release(); e->d_drift[3].release(); e->d_emI[2].release(); e->d_emI[3].release();
+        e->d_fd.release();
+        if (e->h_fd) cudaFreeHost(e->h_fd);
+        e->h_fd = nullptr;
+        e->fd_bytes = 0;
+        e->fd_cached = false;
+        HW_CUDA(e, e->d_fd.ensure(total));
+        HW_CUDA(e, cudaMallocHost((void**)&e->h_fd, total));
+        e->fd_bytes = total;
+        e->d_drift[2].set_view(reinterpret_cast<float2*>(e->d_fd.p), n + 2);
+        e->d_drift[3].set_view(reinterpret_cast<float2*>(e->d_fd.p + sz_d), n + 2);
+        e->d_emI[2].set_view(reinterpret_cast<float*>(e->d_fd.p + 2 * sz_d), nm);
+        e->d_emI[3].set_view(reinterpret_cast<float*>(e->d_fd.p + 2 * sz_d + sz_e), nm);
+    }
+    if (!(e->fd_cached && e->fd_sig[0] == sig_m && e->fd_sig[1] == sig_p)) {
+        HW_CUDA(e, cudaEventSynchronize(e->ev_fd));   // a previous upload may still read the pinned mirror
+        memset(e->h_fd, 0, total);
+        std::vector<float> tab(n);
+        for (int k = 0; k < 2; ++k) {
+            host_shifted_drift_table(e->p, k ? sig_p : sig_m, e->p.sigma, tab.data());
+            float2* dup = reinterpret_cast<float2*>(e->h_fd + k * sz_d);
+            for (int i = 0; i < n; ++i) dup[i] = make_float2(tab[i], tab[i]);
+            build_det_tables(e, 2 + k, tab.data(), reinterpret_cast<float*>(e->h_fd + 2 * sz_d + k * sz_e));
+        }
+        e->fd_sig[0] = sig_m;
+        e->fd_sig[1] = sig_p;
+        e->fd_cached = true;
+    }
+    HW_CUDA(e, cudaMemcpyAsync(e->d_fd.p, e->h_fd, total, cudaMemcpyHostToDevice, e->stream));
+    HW_CUDA(e, cudaEventRecord(e->ev_fd, e->stream));
+    return HW1F_OK;
 }
 
 ModelDev model_dev(const hw1f_engine* e)
@@ -406,14 +448,17 @@ int launch_plans(hw1f_engine* e, const ScenDev* sc, int n_scen, float S1, float 
     return check_launch(e, "bond_plan_kernel");
 }
 
-int upload_market(hw1f_engine* e, int set, const float* P_mkt, const float* f_mkt)
+// market set `set` (0 or 1) <- (P_mkt, f_mkt); both = true fills sets 0 AND 1 with the same curves in one copy
+int upload_market(hw1f_engine* e, int set, const float* P_mkt, const float* f_mkt, bool both = false)
 {
     const int n = e->p.n_mat;
     HW_CUDA(e, e->d_mkt.ensure(4 * (size_t)n));
-    std::vector<float> tmp(2 * (size_t)n);
-    memcpy(tmp.data(), P_mkt, n * sizeof(float));
-    memcpy(tmp.data() + n, f_mkt, n * sizeof(float));
-    return upload(e, e->d_mkt.p + 2 * (size_t)set * n, tmp.data(), tmp.size() * sizeof(float));
+    std::vector<float> tmp((both ? 4 : 2) * (size_t)n);
+    for (int k = 0; k < (both ? 2 : 1); ++k) {
+        memcpy(tmp.data() + 2 * (size_t)k * n, P_mkt, n * sizeof(float));
+        memcpy(tmp.data() + 2 * (size_t)k * n + n, f_mkt, n * sizeof(float));
+    }
+    return upload(e, e->d_mkt.p + (both ? 0 : 2 * (size_t)set * n), tmp.data(), tmp.size() * sizeof(float));
 }
 
 ScenDev scen_dev(const hw1f_engine* e, float sigma, float sig_st, int drift_slot)
@@ -755,7 +800,8 @@ int hw1f_engine_create(int device, hw1f_engine** out)
     if (cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreate(&e->ev0) != cudaSuccess || cudaEventCreate(&e->ev1) != cudaSuccess ||
         cudaEventCreateWithFlags(&e->ev_stage, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&e->ev_model, cudaEventDisableTiming) != cudaSuccess) {
+        cudaEventCreateWithFlags(&e->ev_model, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&e->ev_fd, cudaEventDisableTiming) != cudaSuccess) {
         delete e;
         return HW1F_ERR_CUDA;
     }
@@ -780,8 +826,11 @@ int hw1f_engine_destroy(hw1f_engine* e)
     for (auto& d : e->d_emI) d.release(); e->d_partials.release(); e->d_moments.release();
     e->d_out.release(); e->d_int.release();
     e->d_model.release();
+    e->d_fd.release();
     if (e->h_model) cudaFreeHost(e->h_model);
+    if (e->h_fd) cudaFreeHost(e->h_fd);
     if (e->ev_model) cudaEventDestroy(e->ev_model);
+    if (e->ev_fd) cudaEventDestroy(e->ev_fd);
     if (e->h_stage) cudaFreeHost(e->h_stage);
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
@@ -900,6 +949,8 @@ int hw1f_set_model(hw1f_engine* e, const hw1f_params* p)
         for (int k = 0; k < nm; ++k) cen[k] = 2.0f * emI[k];
         e->cached_p = *p;
         e->model_cached = true;
+        e->fd_cached = false;      // the bumped-sigma tables and the step probe depend on the model
+        e->steps_cached = false;
     }
     e->has_model = true;
     // compute_constants(): ONE host->device copy of the model tables (every call, like the reference's
@@ -938,6 +989,7 @@ int hw1f_steps_to(hw1f_engine* e, float S1, int32_t* n)
 {
     HW_TRY(require_model(e));
     if (!n) return HW1F_ERR_INVALID;
+    if (e->steps_cached && e->steps_S1 == S1 && e->steps_dt == e->dt) { *n = e->steps_n; return HW1F_OK; }
     HW_CUDA(e, cudaSetDevice(e->device));
     HW_CUDA(e, e->d_int.ensure(4));
     steps_probe_kernel<<<1, 1, 0, e->stream>>>(S1, e->dt, e->d_int.p);
@@ -945,6 +997,10 @@ int hw1f_steps_to(hw1f_engine* e, float S1, int32_t* n)
     int v = 0;
     HW_TRY(download(e, &v, e->d_int.p, sizeof(int)));
     *n = v;
+    e->steps_cached = true;    // the device expression is a pure function of (S1, dt)
+    e->steps_S1 = S1;
+    e->steps_dt = e->dt;
+    e->steps_n = v;
     return HW1F_OK;
 }
 
@@ -1255,13 +1311,8 @@ int hw1f_vega_fd(hw1f_engine* e, hw1f_rng* rng, float S1, float S2, float K, con
     // run_finite_difference, src/3:400-446: sigma -/+ eps, sig_st and shifted drift per bump;
     // both bumps read the same market curves and the same normals
     const float sig_m = e->p.sigma - eps, sig_p = e->p.sigma + eps;
-    std::vector<float> tab(e->p.n_steps);
-    host_shifted_drift_table(e->p, sig_m, e->p.sigma, tab.data());
-    HW_TRY(upload_drift(e, 2, tab.data()));
-    host_shifted_drift_table(e->p, sig_p, e->p.sigma, tab.data());
-    HW_TRY(upload_drift(e, 3, tab.data()));
-    HW_TRY(upload_market(e, 0, P_mkt, f_mkt));
-    HW_TRY(upload_market(e, 1, P_mkt, f_mkt));
+    HW_TRY(upload_fd_tables(e, sig_m, sig_p));
+    HW_TRY(upload_market(e, 0, P_mkt, f_mkt, true));
     ScenDev sc[2] = {scen_dev(e, sig_m, host_sig_st(e->p, sig_m), 2), scen_dev(e, sig_p, host_sig_st(e->p, sig_p), 3)};
     HW_TRY(warm_geometry(e, rng));
     HW_CUDA(e, cudaEventRecord(e->ev0, e->stream));
@@ -1322,9 +1373,9 @@ int hw1f_vega_fd_recalibrated(hw1f_engine* e, hw1f_rng* rng, float S1, float S2,
     HW_CUDA(e, cudaEventRecord(e->ev1, e->stream));
     double mom[10];
     HW_TRY(download(e, mom, e->d_moments.p, sizeof(mom)));
-    float P0S2[2];
-    for (int s = 0; s < 2; ++s)
-        HW_TRY(download(e, &P0S2[s], e->d_mkt.p + 2 * (size_t)s * nm + (nm - 1), sizeof(float)));
+    std::vector<float> mk(4 * (size_t)nm);   // both recalibrated curves in one read-back
+    HW_TRY(download(e, mk.data(), e->d_mkt.p, mk.size() * sizeof(float)));
+    const float P0S2[2] = {mk[nm - 1], mk[2 * (size_t)nm + nm - 1]};
     rng->offset += (uint64_t)n;   // the reference leaves d_states after run_zbc_price (src/3:509-510)
     out->n_steps_S1 = n;
     out->price_minus_recal = zbc_price_cv(mom, rng->n_paths, P0S2[0]);
@@ -1367,11 +1418,7 @@ static int fused_launch(hw1f_engine* e, hw1f_rng* rng, float S1, float S2, float
     HW_TRY(launch_plans(e, sc, 1, S1, S2));
     if (fd) {   // run_finite_difference's scenarios (src/3:414-435): sigma -/+ eps, shifted drift, same curves
         const float sig_m = e->p.sigma - eps, sig_p = e->p.sigma + eps;
-        std::vector<float> tab(e->p.n_steps);
-        host_shifted_drift_table(e->p, sig_m, e->p.sigma, tab.data());
-        HW_TRY(upload_drift(e, 2, tab.data()));
-        host_shifted_drift_table(e->p, sig_p, e->p.sigma, tab.data());
-        HW_TRY(upload_drift(e, 3, tab.data()));
+        HW_TRY(upload_fd_tables(e, sig_m, sig_p));
         HW_TRY(upload_market(e, 1, P_mkt, f_mkt));
         sc[1] = scen_dev(e, sig_m, host_sig_st(e->p, sig_m), 2);
         sc[2] = scen_dev(e, sig_p, host_sig_st(e->p, sig_p), 3);
