@@ -85,6 +85,7 @@ struct hw1f_engine {
     DevBuf<float> d_emI[4];              // [n_mat] exp(-det_I) at the save points (decomposed curve kernels)
     DevBuf<BondPlan> d_plans;
     DevBuf<double> d_partials;
+    DevBuf<float2> d_state;              // dumped noise state (h, q) per subsequence (recalibrated FD, one pass)
     DevBuf<double> d_moments;            // internal moment vector
     DevBuf<float> d_out;                 // epilogue outputs
     DevBuf<int> d_int;
@@ -538,7 +539,9 @@ cudaError_t opt_in(K kernel, size_t bytes)
 }
 
 // ---- Q1 launch: sums for NSCEN scenarios into d_moments[n_runs][nscen*2*n_mat] -----------------
-int launch_curve(hw1f_engine* e, const Launch& L, const ScenDev* sc, int nscen, double* d_moments)
+// dump_steps > 0 (decomposed mode, two scenarios, dump_steps on a save point): the kernel also stores the noise
+// state of every subsequence at that step into e->d_state (see fast_kernel DUMP)
+int launch_curve(hw1f_engine* e, const Launch& L, const ScenDev* sc, int nscen, double* d_moments, int dump_steps = 0)
 {
     const int nm = e->p.n_mat, nq = nscen * 2 * nm;
     HW_CUDA(e, e->d_partials.ensure((size_t)L.n_runs * L.grid_x * nq));
@@ -551,11 +554,17 @@ int launch_curve(hw1f_engine* e, const Launch& L, const ScenDev* sc, int nscen, 
         if (nscen == 1) {
             HW_TRY(set_smem(e, fast_kernel<1, 0, 0>, smem));
             fast_kernel<1, 0, 0><<<grid, kThreads, smem, e->stream>>>(L.g, L.seeds, model_dev(e), c0, c1, c0, c0, c0, tg,
-                                                                     e->d_plans.p, 0, 0, 0.f, e->d_partials.p);
+                                                                     e->d_plans.p, 0, 0, 0.f, e->d_partials.p, nullptr);
+        } else if (dump_steps > 0) {
+            HW_CUDA(e, e->d_state.ensure((size_t)L.n_runs * L.g.n_chunks * kChunk));
+            HW_TRY(set_smem(e, (fast_kernel<2, 0, 0, 1>), smem));
+            fast_kernel<2, 0, 0, 1><<<grid, kThreads, smem, e->stream>>>(L.g, L.seeds, model_dev(e), c0, c1, c0, c0, c0, tg,
+                                                                        e->d_plans.p, dump_steps, 0, 0.f, e->d_partials.p,
+                                                                        e->d_state.p);
         } else {
             HW_TRY(set_smem(e, fast_kernel<2, 0, 0>, smem));
             fast_kernel<2, 0, 0><<<grid, kThreads, smem, e->stream>>>(L.g, L.seeds, model_dev(e), c0, c1, c0, c0, c0, tg,
-                                                                     e->d_plans.p, 0, 0, 0.f, e->d_partials.p);
+                                                                     e->d_plans.p, 0, 0, 0.f, e->d_partials.p, nullptr);
         }
         HW_TRY(check_launch(e, "fast_kernel<curve>"));
         reduce_curve_kernel<<<dim3(nm, L.n_runs * nscen), 256, 0, e->stream>>>(
@@ -593,11 +602,11 @@ int launch_zbc(hw1f_engine* e, const Launch& L, const ScenDev* sc, int nscen, in
         if (nscen == 1) {
             HW_TRY(set_smem(e, fast_kernel<0, 1, 0>, smemf));
             fast_kernel<0, 1, 0><<<grid, kThreads, smemf, e->stream>>>(L.g, L.seeds, model_dev(e), z0, z0, z0, z1, z1, tg,
-                                                                      e->d_plans.p, n_steps_S1, L.lead, K, e->d_partials.p);
+                                                                      e->d_plans.p, n_steps_S1, L.lead, K, e->d_partials.p, nullptr);
         } else {
             HW_TRY(set_smem(e, fast_kernel<0, 2, 0>, smemf));
             fast_kernel<0, 2, 0><<<grid, kThreads, smemf, e->stream>>>(L.g, L.seeds, model_dev(e), z0, z0, z0, z1, z1, tg,
-                                                                      e->d_plans.p, n_steps_S1, L.lead, K, e->d_partials.p);
+                                                                      e->d_plans.p, n_steps_S1, L.lead, K, e->d_partials.p, nullptr);
         }
         HW_TRY(check_launch(e, "fast_kernel<zbc>"));
         return reduce_to(e, L.n_runs, L.grid_x, nq, d_moments);
@@ -616,6 +625,20 @@ int launch_zbc(hw1f_engine* e, const Launch& L, const ScenDev* sc, int nscen, in
     return reduce_to(e, L.n_runs, L.grid_x, nq, d_moments);
 }
 
+// the two ZBC scenarios evaluated on the noise state a preceding launch_curve(.., dump_steps = n_steps_S1) left in
+// e->d_state: same moments as launch_zbc on the same normals, without simulating them again
+int launch_zbc_from_state(hw1f_engine* e, const Launch& L, const ScenDev* sc, int n_steps_S1, float K, double* d_moments)
+{
+    const int nq = 10;
+    HW_CUDA(e, e->d_partials.ensure((size_t)L.n_runs * L.grid_x * nq));
+    const FastScen z0 = fast_scen(e, sc[0].sig_st, drift_slot_of(e, sc[0]), n_steps_S1);
+    const FastScen z1 = fast_scen(e, sc[1].sig_st, drift_slot_of(e, sc[1]), n_steps_S1);
+    zbc_from_state_kernel<2><<<dim3(L.grid_x, L.n_runs), kThreads, 0, e->stream>>>(L.g, z0, z1, e->d_plans.p, K, e->d_state.p,
+                                                                                  e->d_partials.p);
+    HW_TRY(check_launch(e, "zbc_from_state_kernel"));
+    return reduce_to(e, L.n_runs, L.grid_x, nq, d_moments);
+}
+
 int launch_pathwise(hw1f_engine* e, const Launch& L, const ScenDev& sc, int n_steps_S1, float K, double* d_moments)
 {
     HW_CUDA(e, e->d_partials.ensure((size_t)L.n_runs * L.grid_x * 3));
@@ -625,7 +648,7 @@ int launch_pathwise(hw1f_engine* e, const Launch& L, const ScenDev& sc, int n_st
         const size_t smemf = smem_fast(e, 0);
         HW_TRY(set_smem(e, fast_kernel<0, 0, 1>, smemf));
         fast_kernel<0, 0, 1><<<dim3(L.grid_x, L.n_runs), kThreads, smemf, e->stream>>>(
-            L.g, L.seeds, model_dev(e), z0, z0, z0, z0, z0, tg, e->d_plans.p, n_steps_S1, L.lead, K, e->d_partials.p);
+            L.g, L.seeds, model_dev(e), z0, z0, z0, z0, z0, tg, e->d_plans.p, n_steps_S1, L.lead, K, e->d_partials.p, nullptr);
         HW_TRY(check_launch(e, "fast_kernel<pathwise>"));
         return reduce_range(e, L.n_runs, L.grid_x, 3, 0, 2, d_moments, 2);
     }
@@ -698,6 +721,7 @@ int init_kernels(hw1f_engine* e)
     HW_CUDA(e, opt_in(fused_kernel<true>, b));
     HW_CUDA(e, opt_in(fast_kernel<1, 0, 0>, b));
     HW_CUDA(e, opt_in(fast_kernel<2, 0, 0>, b));
+    HW_CUDA(e, opt_in((fast_kernel<2, 0, 0, 1>), b));
     HW_CUDA(e, opt_in(fast_kernel<0, 1, 0>, b));
     HW_CUDA(e, opt_in(fast_kernel<0, 2, 0>, b));
     HW_CUDA(e, opt_in(fast_kernel<0, 0, 1>, b));
@@ -715,6 +739,7 @@ int init_kernels(hw1f_engine* e)
     HW_CUDA(e, cudaFuncGetAttributes(&attr, bond_plan_kernel));
     HW_CUDA(e, cudaFuncGetAttributes(&attr, reduce_partials_kernel<double>));
     HW_CUDA(e, cudaFuncGetAttributes(&attr, reduce_curve_kernel));
+    HW_CUDA(e, cudaFuncGetAttributes(&attr, zbc_from_state_kernel<2>));
     HW_CUDA(e, cudaFuncGetAttributes(&attr, curve_epilogue_kernel));
     HW_CUDA(e, cudaFuncGetAttributes(&attr, theta_kernel));
     HW_CUDA(e, cudaFuncGetAttributes(&attr, fused_uncenter_kernel));
@@ -823,7 +848,7 @@ int hw1f_engine_destroy(hw1f_engine* e)
     e->d_Jpow2.release(); e->d_W.release(); e->d_U.release();
     for (auto& d : e->d_drift) d.release();
     e->d_mkt.release(); e->d_center.release(); e->d_plans.release();
-    for (auto& d : e->d_emI) d.release(); e->d_partials.release(); e->d_moments.release();
+    for (auto& d : e->d_emI) d.release(); e->d_partials.release(); e->d_moments.release(); e->d_state.release();
     e->d_out.release(); e->d_int.release();
     e->d_model.release();
     e->d_fd.release();
@@ -1360,7 +1385,11 @@ int hw1f_vega_fd_recalibrated(hw1f_engine* e, hw1f_rng* rng, float S1, float S2,
     HW_CUDA(e, cudaEventRecord(e->ev0, e->stream));
     Launch L;
     HW_TRY(prepare_launch(e, &rng->seed, 1, rng->first_path, rng->n_paths, rng->offset, &L));
-    HW_TRY(launch_curve(e, L, sc, 2, e->d_moments.p));
+    // decomposed mode, S1 on the maturity grid: the curve pass parks every subsequence's noise state at step n, and
+    // the two prices are evaluated from it once the recalibrated curves exist -- normals [off, off+n) are the first
+    // n normals of the curve window, so nothing is simulated twice.  Otherwise: second pass over [off, off+n).
+    const bool one_pass = e->mode == HW1F_MODE_DECOMPOSED && n > 0 && (n % e->stride) == 0;
+    HW_TRY(launch_curve(e, L, sc, 2, e->d_moments.p, one_pass ? n : 0));
     const float inv_dT = 1.0f / e->spacing;
     for (int s = 0; s < 2; ++s) {
         float* dP = e->d_mkt.p + 2 * (size_t)s * nm;
@@ -1369,7 +1398,8 @@ int hw1f_vega_fd_recalibrated(hw1f_engine* e, hw1f_rng* rng, float S1, float S2,
         HW_TRY(check_launch(e, "curve_epilogue_kernel"));
     }
     HW_TRY(launch_plans(e, sc, 2, S1, S2));
-    HW_TRY(launch_zbc(e, L, sc, 2, n, K, e->d_moments.p));
+    if (one_pass) HW_TRY(launch_zbc_from_state(e, L, sc, n, K, e->d_moments.p));
+    else HW_TRY(launch_zbc(e, L, sc, 2, n, K, e->d_moments.p));
     HW_CUDA(e, cudaEventRecord(e->ev1, e->stream));
     double mom[10];
     HW_TRY(download(e, mom, e->d_moments.p, sizeof(mom)));
@@ -1442,11 +1472,11 @@ static int fused_launch(hw1f_engine* e, hw1f_rng* rng, float S1, float S2, float
         if (fd) {
             HW_TRY(set_smem(e, fast_kernel<1, 3, 2>, smemf));
             fast_kernel<1, 3, 2><<<L.grid_x, kThreads, smemf, e->stream>>>(L.g, L.seeds, model_dev(e), c0, c0, c0, zm, zp, tg,
-                                                                          e->d_plans.p, n, 0, K, e->d_partials.p);
+                                                                          e->d_plans.p, n, 0, K, e->d_partials.p, nullptr);
         } else {
             HW_TRY(set_smem(e, fast_kernel<1, 1, 2>, smemf));
             fast_kernel<1, 1, 2><<<L.grid_x, kThreads, smemf, e->stream>>>(L.g, L.seeds, model_dev(e), c0, c0, c0, c0, c0, tg,
-                                                                          e->d_plans.p, n, 0, K, e->d_partials.p);
+                                                                          e->d_plans.p, n, 0, K, e->d_partials.p, nullptr);
         }
         HW_TRY(check_launch(e, "fast_kernel<fused>"));
         reduce_curve_kernel<<<dim3(nm, 1), 256, 0, e->stream>>>(e->d_partials.p, (int)L.grid_x, nq, 1, nm, c0.emI, c0.emI,

@@ -37,9 +37,34 @@ struct FastState {
     __device__ __forceinline__ float2 q() const { return fma2(S, splat(2.0f), make_float2(-h.x, -h.y)); }
 };
 
+// ZBC payoff X and control Y of both antithetic twins of both lanes for one sigma scenario, from the shared
+// noise state (h, q) at S1:  r(+/-) = mS1 +/- sg h,  I(+/-) = ImS1 +/- c q.  mom5 = per-lane pair sums
+// {X1+X2, Y1+Y2, X1^2+X2^2, Y1^2+Y2^2, X1 Y1 + X2 Y2} (common.cuh:356-362)
+__device__ __forceinline__ void fast_zbc_mom5(float2 h, float2 q, const FastScen& z, const BondPlan& plan, float K,
+                                              float2 (&mom5)[5])
+{
+    PairState ps;
+    const float2 dr = mul2(h, splat(z.sg)), dI = mul2(q, splat(z.c));
+    ps.r1 = add2(splat(z.mS1), dr);
+    ps.r2 = add2(splat(z.mS1), make_float2(-dr.x, -dr.y));
+    ps.I1 = add2(splat(z.ImS1), dI);
+    ps.I2 = add2(splat(z.ImS1), make_float2(-dI.x, -dI.y));
+    float2 x1, x2, c1, c2;
+    zbc_payoffs(ps, plan, K, x1, x2, c1, c2);
+    mom5[0] = add2(x1, x2);
+    mom5[1] = add2(c1, c2);
+    mom5[2] = fma2(x1, x1, mul2(x2, x2));
+    mom5[3] = fma2(c1, c1, mul2(c2, c2));
+    mom5[4] = fma2(c1, x1, mul2(c2, x2));
+}
+
 // NCUR  : number of curve scenarios accumulated on the maturity grid (0, 1, 2)
 // NZBC  : number of ZBC scenarios evaluated at S1 (0..3); plans[0..NZBC)
 // PW    : 0 none, 1 pathwise vega of the +G path only (the reference's estimator), 2 both twins
+// DUMP  : 1 = also store the noise state (h, q) of every subsequence at step n_steps_S1 (a save point) to
+//         dump[run][chunk * kChunk + {tid, tid + kThreads}] as float4 (h_A, q_A, h_B, q_B) halves, so that payoffs
+//         whose constants depend on THIS pass's curve (recalibrated FD, src/3:484-525) are evaluated afterwards
+//         by zbc_from_state_kernel without simulating the same normals again
 // partials[run][block][NCUR*2*n_mat + NZBC*5 + (PW ? 3 : 0)] doubles; the S1 block is laid out as
 // [ZBC scenario 0 (5)] [pathwise (3)] [ZBC scenarios 1.. (5 each)]  == the hw1f_fused* ABI order
 template <int NZBC, int PW>
@@ -47,14 +72,14 @@ __device__ __forceinline__ constexpr int ext_zbc(int s) { return s == 0 ? 0 : 5 
 template <int NZBC, int PW>
 __device__ __forceinline__ constexpr int ext_pw() { return NZBC > 0 ? 5 : 0; }
 
-template <int NCUR, int NZBC, int PW>
+template <int NCUR, int NZBC, int PW, int DUMP = 0>
 #ifndef HW1F_FAST_MIN_BLOCKS
 #define HW1F_FAST_MIN_BLOCKS 2   // A/B in profiles/r01_ab_variants_decomposed.txt: 512 threads x 2 blocks (64 regs) is best
 #endif
 __global__ void __launch_bounds__(kThreads, HW1F_FAST_MIN_BLOCKS)
 fast_kernel(StreamGeom g, SeedArgs seeds, ModelDev md, FastScen cs0, FastScen cs1, FastScen zs0, FastScen zs1,
             FastScen zs2, FastTangent tg, const BondPlan* __restrict__ plans, int n_steps_S1, int lead, float K,
-            double* __restrict__ partials)
+            double* __restrict__ partials, float2* __restrict__ dump)
 {
     extern __shared__ __align__(16) uint32_t smem[];
     constexpr int kS1 = NZBC * 5 + (PW ? 3 : 0);
@@ -125,16 +150,8 @@ fast_kernel(StreamGeom g, SeedArgs seeds, ModelDev md, FastScen cs0, FastScen cs
 #pragma unroll
             for (int s = 0; s < NZBC; ++s) {
                 const FastScen z = (s == 0) ? zs0 : (s == 1 ? zs1 : zs2);
-                PairState ps;
-                const float2 dr = mul2(st.h, splat(z.sg)), dI = mul2(q, splat(z.c));
-                ps.r1 = add2(splat(z.mS1), dr);
-                ps.r2 = add2(splat(z.mS1), make_float2(-dr.x, -dr.y));
-                ps.I1 = add2(splat(z.ImS1), dI);
-                ps.I2 = add2(splat(z.ImS1), make_float2(-dI.x, -dI.y));
-                float2 x1, x2, c1, c2;
-                zbc_payoffs(ps, plans[s], K, x1, x2, c1, c2);
-                const float2 mom5[5] = {add2(x1, x2), add2(c1, c2), fma2(x1, x1, mul2(x2, x2)),
-                                        fma2(c1, c1, mul2(c2, c2)), fma2(c1, x1, mul2(c2, x2))};
+                float2 mom5[5];
+                fast_zbc_mom5(st.h, q, z, plans[s], K, mom5);
 #pragma unroll
                 for (int k = 0; k < 5; ++k) {
                     const double w = warp_sum((double)mom5[k].x * mA + (double)mom5[k].y * mB);
@@ -186,6 +203,12 @@ fast_kernel(StreamGeom g, SeedArgs seeds, ModelDev md, FastScen cs0, FastScen cs
                 advance_pairs(t, pair, half, pairfn);
                 save_curve(m);
                 if (kS1 > 0 && m == m_S1) eval_S1();
+                if (DUMP && m == m_S1) {
+                    float2* d = dump + ((size_t)run * g.n_chunks + chunk) * kChunk + tid;
+                    const float2 q = st.q();
+                    d[0] = make_float2(st.h.x, q.x);
+                    d[kThreads] = make_float2(st.h.y, q.y);
+                }
             }
         } else {
             const int n_main = n_total - lead;
@@ -223,6 +246,48 @@ fast_kernel(StreamGeom g, SeedArgs seeds, ModelDev md, FastScen cs0, FastScen cs
     if (NCUR)
         for (int k = tid; k < nqc; k += kThreads) out[k] = bacc[k];
     if (kS1 > 0 && tid < kS1) out[nqc + tid] = bext[tid];
+}
+
+// ZBC/control moments of NZBC sigma scenarios from a dumped noise state (see DUMP above): no RNG, no recursion.
+// Same thread <-> subsequence mapping, validity masks, warp/block reduction order and partials layout
+// (partials[run][block][5 * NZBC]) as fast_kernel<0, NZBC, 0>, so reduce_partials_kernel finishes it.
+template <int NZBC>
+__global__ void __launch_bounds__(kThreads)
+zbc_from_state_kernel(StreamGeom g, FastScen zs0, FastScen zs1, const BondPlan* __restrict__ plans, float K,
+                      const float2* __restrict__ dump, double* __restrict__ partials)
+{
+    constexpr int kS1 = NZBC * 5;
+    __shared__ double wext[kWarps][kS1];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int run = blockIdx.y;
+    double acc = 0.0;   // threads 0 .. kS1-1 own one moment each
+    for (unsigned long long chunk = blockIdx.x; chunk < g.n_chunks; chunk += gridDim.x) {
+        const unsigned long long pA = ((g.chunk0 + chunk) << kChunkLog2) + tid, pB = pA + kThreads;
+        const double mA = (pA >= g.first_path && pA < g.first_path + g.n_paths) ? 1.0 : 0.0;
+        const double mB = (pB >= g.first_path && pB < g.first_path + g.n_paths) ? 1.0 : 0.0;
+        const float2* d = dump + ((size_t)run * g.n_chunks + chunk) * kChunk + tid;
+        const float2 sA = d[0], sB = d[kThreads];
+        const float2 h = make_float2(sA.x, sB.x), q = make_float2(sA.y, sB.y);
+        __syncthreads();   // wext of the previous chunk has been consumed
+#pragma unroll
+        for (int s = 0; s < NZBC; ++s) {
+            float2 mom5[5];
+            fast_zbc_mom5(h, q, s ? zs1 : zs0, plans[s], K, mom5);
+#pragma unroll
+            for (int k = 0; k < 5; ++k) {
+                const double w = warp_sum((double)mom5[k].x * mA + (double)mom5[k].y * mB);
+                if (lane == 0) wext[warp][5 * s + k] = w;
+            }
+        }
+        __syncthreads();
+        if (tid < kS1) {
+            double a = wext[0][tid];
+#pragma unroll
+            for (int w = 1; w < kWarps; ++w) a += wext[w][tid];
+            acc += a;
+        }
+    }
+    if (tid < kS1) partials[((size_t)run * gridDim.x + blockIdx.x) * kS1 + tid] = acc;
 }
 
 }  // namespace hw1f

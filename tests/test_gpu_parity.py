@@ -167,19 +167,40 @@ def test_vega_fd_vs_oracle(engine, hw, oracle, curve):
     assert got["vega_fd"] == pytest.approx((prices[1] - prices[0]) / (2 * float(eps)), abs=2e-3)
 
 
-def test_vega_fd_recalibrated_vs_oracle(engine, hw, oracle):
+@pytest.mark.parametrize("n_steps", [500, 490, 495])
+def test_vega_fd_recalibrated_vs_oracle(engine, hw, oracle, n_steps):
+    """n_steps on the maturity grid (500, 490): decomposed mode prices from the noise state the curve pass parked
+    (one simulation); 495: off the grid, second pass over the same normals; reference-order mode: always two passes"""
     eps, sig = np.float32(0.001), np.float32(0.1)
     rng = hw.Rng(SEED, N).seek(1000)
-    got = engine.vega_fd_recalibrated(rng, eps=float(eps), n_steps_S1=500)
-    assert rng.tell() == 1500
+    got = engine.vega_fd_recalibrated(rng, eps=float(eps), n_steps_S1=n_steps)
+    assert rng.tell() == 1000 + n_steps
     prices = []
     for s_new in (sig - eps, sig + eps):
         sums, _ = oracle.bond_curve_sums(SEED, N, offset=1000, sigma=float(s_new))     # unshifted base drift
         P, f = oracle.curve_finalize(sums, N)
-        mom = oracle.zbc_moments(SEED, N, P, f, n_steps_S1=500, offset=1000, sigma=float(s_new))
+        mom = oracle.zbc_moments(SEED, N, P, f, n_steps_S1=n_steps, offset=1000, sigma=float(s_new))
         prices.append(oracle.zbc_algebra(mom, 2 * N, float(P[100]))["price_cv"])
     assert got["price_minus_recal"] == pytest.approx(prices[0], rel=5e-5)
     assert got["price_plus_recal"] == pytest.approx(prices[1], rel=5e-5)
+
+
+def test_vega_fd_recalibrated_equals_bumped_engines(engine, hw):
+    """recompute_market_data + run_zbc_price at sigma -/+ eps (src/3:449-525) composed from the public single-scenario
+    calls on engines whose MODEL carries the bumped sigma (the base drift does not depend on sigma): the fused
+    two-scenario launches of hw1f_vega_fd_recalibrated must give the same prices"""
+    eps = 0.001
+    got = engine.vega_fd_recalibrated(hw.Rng(SEED, N).seek(1000), eps=eps, n_steps_S1=500)
+    prices = []
+    for sgn in (-1.0, 1.0):
+        e2 = hw.Engine(device=0, params=hw.default_params(sigma=float(np.float32(0.1) + np.float32(sgn * eps))))
+        e2.set_mode(engine.mode)
+        c = e2.bond_curve(hw.Rng(SEED, N).seek(1000))
+        z = e2.zbc_cv(hw.Rng(SEED, N).seek(1000), c["P"], c["f"], n_steps_S1=500)
+        prices.append(z["price_cv"])
+        e2.close()
+    assert got["price_minus_recal"] == pytest.approx(prices[0], rel=2e-6)
+    assert got["price_plus_recal"] == pytest.approx(prices[1], rel=2e-6)
 
 
 def test_vega_sequence_windows(engine, hw, curve):
