@@ -61,6 +61,7 @@ struct hw1f_multi {
     NcclApi nccl;
     hw1f_params p{};
     bool has_model = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;   // device-0 timing of the multi-GPU calls
     std::string err;
 };
 
@@ -149,6 +150,8 @@ int hw1f_multi_create(int n_gpus, hw1f_multi** out)
         if (cudaStreamCreateWithFlags(&m->stream[d], cudaStreamNonBlocking) != cudaSuccess) { hw1f_multi_destroy(m); return HW1F_ERR_CUDA; }
         hw1f_engine_set_stream(m->eng[d], m->stream[d]);
     }
+    cudaSetDevice(0);
+    if (cudaEventCreate(&m->ev0) != cudaSuccess || cudaEventCreate(&m->ev1) != cudaSuccess) { hw1f_multi_destroy(m); return HW1F_ERR_CUDA; }
     if (n_gpus > 1) {
         std::string err;
         if (!m->nccl.load(err)) { std::fprintf(stderr, "hw1f_multi_create: %s\n", err.c_str()); hw1f_multi_destroy(m); return HW1F_ERR_UNSUPPORTED; }
@@ -176,6 +179,9 @@ int hw1f_multi_destroy(hw1f_multi* m)
         if (m->eng[d]) hw1f_engine_destroy(m->eng[d]);
         if (m->stream[d]) cudaStreamDestroy(m->stream[d]);
     }
+    if (m->n > 0) cudaSetDevice(0);
+    if (m->ev0) cudaEventDestroy(m->ev0);
+    if (m->ev1) cudaEventDestroy(m->ev1);
     if (m->nccl.lib) dlclose(m->nccl.lib);
     delete m;
     return HW1F_OK;
@@ -216,10 +222,8 @@ int hw1f_multi_bond_curve(hw1f_multi* m, uint64_t seed, uint64_t n_paths_total, 
     s = make_rngs(m, seed, n_paths_total, normal_offset, &rngs);
     if (s != HW1F_OK) return s;
     for (int d = 0; d < m->n; ++d) M_ENG(m, d, hw1f_rng_prepare(m->eng[d], rngs.h[d]));
-    cudaEvent_t e0, e1;
+    cudaEvent_t e0 = m->ev0, e1 = m->ev1;
     M_CUDA(m, cudaSetDevice(0));
-    M_CUDA(m, cudaEventCreate(&e0));
-    M_CUDA(m, cudaEventCreate(&e1));
     M_CUDA(m, cudaEventRecord(e0, m->stream[0]));
     for (int d = 0; d < m->n; ++d) M_ENG(m, d, hw1f_bond_curve_moments(m->eng[d], rngs.h[d], m->d_mom[d]));
     s = allreduce(m, count);
@@ -229,8 +233,6 @@ int hw1f_multi_bond_curve(hw1f_multi* m, uint64_t seed, uint64_t n_paths_total, 
     M_ENG(m, 0, hw1f_bond_curve_finish(m->eng[0], m->d_mom[0], n_paths_total, P, f, P_se));
     for (int d = 1; d < m->n; ++d) { M_CUDA(m, cudaSetDevice(d)); M_CUDA(m, cudaStreamSynchronize(m->stream[d])); }
     if (wall_ms) { M_CUDA(m, cudaSetDevice(0)); M_CUDA(m, cudaEventElapsedTime(wall_ms, e0, e1)); }
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
     return HW1F_OK;
 }
 
@@ -273,10 +275,8 @@ int hw1f_multi_fused(hw1f_multi* m, uint64_t seed, uint64_t n_paths_total, uint6
     s = make_rngs(m, seed, n_paths_total, normal_offset, &rngs);
     if (s != HW1F_OK) return s;
     for (int d = 0; d < m->n; ++d) M_ENG(m, d, hw1f_rng_prepare(m->eng[d], rngs.h[d]));
-    cudaEvent_t e0, e1;
+    cudaEvent_t e0 = m->ev0, e1 = m->ev1;
     M_CUDA(m, cudaSetDevice(0));
-    M_CUDA(m, cudaEventCreate(&e0));
-    M_CUDA(m, cudaEventCreate(&e1));
     M_CUDA(m, cudaEventRecord(e0, m->stream[0]));
     for (int d = 0; d < m->n; ++d)
         M_ENG(m, d, hw1f_fused_fd_moments(m->eng[d], rngs.h[d], S1, S2, K, P_mkt, f_mkt, eps, n, m->d_mom[d]));
@@ -292,8 +292,6 @@ int hw1f_multi_fused(hw1f_multi* m, uint64_t seed, uint64_t n_paths_total, uint6
     M_CUDA(m, cudaEventElapsedTime(&ms, e0, e1));
     vega->ms_pathwise = vega->ms_fd = ms;
     if (wall_ms) *wall_ms = ms;
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
     return HW1F_OK;
 }
 
