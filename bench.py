@@ -37,10 +37,13 @@ UNIT = "path-steps/s"
 N_PATHS_LOG2 = 20          # reference N_PATHS = 1024*1024 (include/common.cuh:16)
 # Algorithmic pipe instructions per path-step.
 #   reference-order arithmetic: 6.75 FP32 + 1.0 MUFU + 3.75 INT + 0.5 I2F = 12 issue slots
-#   decomposed arithmetic (default mode)   : 2.5 FP32 + 1.0 MUFU + 3.75 INT + 0.5 I2F = 7.75 issue slots
-#   Q1 adds 4 MUFU.EX2 per 40 path-steps at the save points: 1.1 MUFU per path-step in both modes
+#   decomposed arithmetic (default mode)   : 2.25 FP32 + 1.0 MUFU + 3.75 INT + 0.5 I2F = 7.5 issue slots
+#     (per Box-Muller pair and lane = 4 path-steps: 4 Box-Muller FP32 + 5 for the two-step recursion; the loop
+#      body's SASS is 299 dispatch cycles per 40 path-steps = 7.48)
+#   Q1 save points: reference-order mode adds 4 MUFU.EX2 per 40 path-steps (1.1 MUFU per path-step); decomposed
+#   mode evaluates 2cosh(z)-2 as a polynomial on the FMA pipe (no XU work)
 ALGO = {
-    "decomposed": {"issue": 7.75, "fp32": 2.5, "xu": 1.1},
+    "decomposed": {"issue": 7.5, "fp32": 2.25, "xu": 1.0},
     "reference_order": {"issue": 12.0, "fp32": 6.75, "xu": 1.1},
 }
 

@@ -297,6 +297,14 @@ ModelDev model_dev(const hw1f_engine* e)
     ModelDev m;
     m.r0 = e->p.r0;
     m.exp_adt = e->exp_adt;
+    m.exp_2adt = e->exp_adt * e->exp_adt;
+    {
+        const double ed = (double)e->exp_adt, rho = (ed * ed - (double)m.exp_2adt) / (double)m.exp_2adt;
+        m.rho1 = (float)rho;
+        m.rho5 = (float)(5.0 * rho);
+        m.qA = (float)(2.0 / (1.0 - ed));
+        m.qB = (float)(2.0 * ed / (1.0 - ed) + 1.0);
+    }
     m.dt = e->dt;
     m.a = e->p.a;
     m.spacing = e->spacing;

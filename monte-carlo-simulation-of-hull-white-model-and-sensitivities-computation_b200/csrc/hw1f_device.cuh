@@ -71,8 +71,9 @@ __device__ __forceinline__ float u2f(uint32_t x)
 
 // _curand_box_muller (curand_normal.h:70-87) for two independent streams at once.
 // x = first draw, y = second draw of each stream.  n_sin -> normal 2k, n_cos -> normal 2k+1.
-__device__ __forceinline__ void box_muller2(uint32_t xa, uint32_t ya, uint32_t xb, uint32_t yb,
-                                            float2& n_sin, float2& n_cos)
+// radius and direction separately: s = sqrt(-2 ln u), sn = sin v, cs = cos v (the three MUFU results per lane)
+__device__ __forceinline__ void box_muller2_parts(uint32_t xa, uint32_t ya, uint32_t xb, uint32_t yb,
+                                                  float2& s, float2& sn, float2& cs)
 {
     const float2 fx = make_float2(u2f(xa), u2f(xb));
     const float2 fy = make_float2(u2f(ya), u2f(yb));
@@ -82,9 +83,16 @@ __device__ __forceinline__ void box_muller2(uint32_t xa, uint32_t ya, uint32_t x
     // RN(RN(l*c) * -2) == RN(l * (-2c)) bit for bit (no subnormals can occur: |l*c| >= 5.9e-8 or 0)
     float2 l = make_float2(mufu_lg2(u.x), mufu_lg2(u.y));
     l = mul2(l, splat(kNeg2Ln2));
-    const float2 s = make_float2(mufu_sqrt(l.x), mufu_sqrt(l.y));
-    const float2 sn = make_float2(mufu_sin(v.x), mufu_sin(v.y));
-    const float2 cs = make_float2(mufu_cos(v.x), mufu_cos(v.y));
+    s = make_float2(mufu_sqrt(l.x), mufu_sqrt(l.y));
+    sn = make_float2(mufu_sin(v.x), mufu_sin(v.y));
+    cs = make_float2(mufu_cos(v.x), mufu_cos(v.y));
+}
+
+__device__ __forceinline__ void box_muller2(uint32_t xa, uint32_t ya, uint32_t xb, uint32_t yb,
+                                            float2& n_sin, float2& n_cos)
+{
+    float2 s, sn, cs;
+    box_muller2_parts(xa, ya, xb, yb, s, sn, cs);
     n_sin = mul2(s, sn);
     n_cos = mul2(s, cs);
 }

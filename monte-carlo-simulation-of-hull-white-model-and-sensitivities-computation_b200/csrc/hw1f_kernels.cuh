@@ -50,6 +50,11 @@ struct StreamGeom {
 
 struct ModelDev {
     float r0, exp_adt, dt, a;
+    // decomposed kernels (hw1f_kernels_fast.cuh): exp_2adt = RN(exp_adt^2), the two-step decay as a float;
+    // rho1 / rho5 = the relative residual (exp_adt^2 - exp_2adt)/exp_2adt of that rounding, once and five times
+    // (applied as h += rho h so that the effective decay is exp_adt per step: S is 1/(1-e) times as sensitive to
+    // the decay as h is); q = qA W - qB h with qA = 2/(1-e), qB = 2e/(1-e) + 1, e = exp_adt
+    float exp_2adt, rho1, rho5, qA, qB;
     float inv_spacing, neg_spacing, spacing;
     int n_steps, n_mat, stride;
 };
@@ -257,6 +262,24 @@ __device__ __forceinline__ void advance_pairs(ThreadStreams& t, int& pair, int n
     for (; k < n_pairs; ++k) { run_pairs<1>(t, pair, f); pair += 1; }
 }
 
+// the same walk handing out radius and direction of each pair separately: f(pair_index, s, sin v, cos v)
+// (decomposed kernels fold the products s sin v, s cos v into their fused multiply-adds); j = position in the group
+template <int NP, class PartsFn>
+__device__ __forceinline__ void run_pairs_parts(ThreadStreams& t, int pair, PartsFn&& f)
+{
+#pragma unroll
+    for (int j = 0; j < NP; ++j) {
+        const uint32_t xa = t.A.next() + (t.dcur + kWeyl * (2 * j + 1));
+        const uint32_t xb = t.B.next() + (t.dcurB + kWeyl * (2 * j + 1));
+        const uint32_t ya = t.A.next() + (t.dcur + kWeyl * (2 * j + 2));
+        const uint32_t yb = t.B.next() + (t.dcurB + kWeyl * (2 * j + 2));
+        float2 s, sn, cs;
+        box_muller2_parts(xa, ya, xb, yb, s, sn, cs);
+        f(j, s, sn, cs);
+    }
+    t.dcur += kWeyl * (2 * NP);
+    t.dcurB += kWeyl * (2 * NP);
+}
 // one isolated pair (lead / tail handling of odd normal offsets and odd step counts)
 __device__ __forceinline__ void one_pair(ThreadStreams& t, float2& ns, float2& nc)
 {

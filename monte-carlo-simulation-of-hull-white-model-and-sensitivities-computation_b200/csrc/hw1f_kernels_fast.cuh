@@ -10,11 +10,22 @@
 //     I(+/-)  = Im_i     +/- (dt/2) sig_st q_i   (trapezoid of the noise part: sum (h_i + h_{i+1}))
 //     tangent = D_i      + (sig_st/sigma) h_i ,  its integral = ID_i + (dt/2)(sig_st/sigma) q_i
 //
-// Two packed FP32 instructions per time step for BOTH antithetic twins of BOTH lanes (and for any
-// number of sigma scenarios), instead of eight.  Same XORWOW integers and same Box-Muller floats as
-// the reference-order kernels; the per-path floats differ from the reference by rounding only
-// (~1e-7 relative), far inside the 1e-5 north-star tolerance -- tests run both modes against the
-// oracle and against the reference binaries.
+// Instead of S the kernels carry W_n = sum_{i<n} G_i (no dependence on h): summing the recursion gives
+// S_n (1 - e) = W_n - e h_n, hence q_n = qA W_n - qB h_n with qA = 2/(1-e), qB = 2e/(1-e) + 1.  A Box-Muller pair
+// (G1, G2) = s (sin v, cos v) then advances two steps with FIVE packed instructions:
+//     a = e sin v + cos v,  b = sin v + cos v,  h <- e^2 h + s a,  W <- W + s b
+// (e^2 is not a float: the kernels multiply by RN(e^2) and add the relative residual back once per five pairs,
+// h += 5 rho h -- S responds to the decay 1/(1-e) ~ 100 times as strongly as h, so the half-ulp matters)
+// i.e. 2.5 packed FP32 instructions per time step for BOTH antithetic twins of BOTH lanes (and for any
+// number of sigma scenarios), instead of eight.  Same XORWOW integers and the same three Box-Muller floats per
+// pair (s = sqrt(-2 ln u), sin v, cos v: the MUFU results) as the reference-order kernels; the products
+// s sin v, s cos v enter through the fused multiply-adds above instead of being rounded on their own, so the
+// per-path floats differ from the reference by rounding only (~1e-7 relative), far inside the 1e-5 north-star
+// tolerance -- tests run both modes against the oracle and against the reference binaries.
+//
+// Curve save points: p0 = e^{-I+} + e^{-I-} = e^{-Im} (2 + d) with d = 2 cosh(z) - 2, z = c q the noise part of
+// the integral.  d is evaluated as z^2 times a degree-4 polynomial in z^2 (no XU work, no cancellation at short
+// maturities); a warp holding a |z| > 1.2 falls back to ex2(+/-z log2 e).
 #pragma once
 #include "hw1f_kernels_extra.cuh"
 
@@ -37,8 +48,8 @@ struct FastTangent {
 #endif
 
 struct FastState {
-    float2 h, S;
-    __device__ __forceinline__ float2 q() const { return fma2(S, splat(2.0f), make_float2(-h.x, -h.y)); }
+    float2 h, W;
+    __device__ __forceinline__ float2 q(float qA, float qB) const { return fma2(W, splat(qA), mul2(h, splat(-qB))); }
 };
 
 // ZBC payoff X and control Y of both antithetic twins of both lanes for one sigma scenario, from the shared
@@ -109,7 +120,7 @@ fast_kernel(StreamGeom g, SeedArgs seeds, ModelDev md, FastScen cs0, FastScen cs
     }
     if (kS1 > 0 && tid < kS1) bext[tid] = 0.0;
 
-    const float2 e2 = splat(md.exp_adt);
+    const float2 e2 = splat(md.exp_adt), ee2 = splat(md.exp_2adt);
     const int half = md.stride >> 1;
     const int n_total = NCUR ? md.n_steps : n_steps_S1;
     const int m_S1 = NCUR ? n_steps_S1 / md.stride : 0;
@@ -118,23 +129,51 @@ fast_kernel(StreamGeom g, SeedArgs seeds, ModelDev md, FastScen cs0, FastScen cs
     float* const wrow = wflt + warp * nqc + ((lane & 16) ? n_mat : 0);
     // per-scenario exponents: exp(-/+ c q) = ex2(-/+ q * (c log2e))
     const float kc0 = mul_(cs0.c, kLog2e), kc1 = mul_(cs1.c, kLog2e);
+    const float zA0 = mul_(cs0.c, md.qA), zB0 = -mul_(cs0.c, md.qB), zA1 = mul_(cs1.c, md.qA), zB1 = -mul_(cs1.c, md.qB);
 
     for (unsigned long long chunk = blockIdx.x; chunk < g.n_chunks; chunk += gridDim.x) {
         ThreadStreams t = derive_streams(g, seeds, run, chunk, win);
         FastState st;
         st.h = splat(0.0f);
-        st.S = splat(0.0f);
+        st.W = splat(0.0f);
         const float2 mask = make_float2(t.validA ? 1.0f : 0.0f, t.validB ? 1.0f : 0.0f);
         const bool full = __syncthreads_and(t.validA && t.validB);
 
-        auto step1 = [&](float2 G) {
+        int pair = 0;
+        auto step1 = [&](float2 G) {       // single step (odd lead / tail only)
+            st.W = add2(st.W, G);
             st.h = fma2(st.h, e2, G);
-            st.S = add2(st.S, st.h);
         };
-        auto pairfn = [&](int, float2 ns, float2 nc) { step1(ns); step1(nc); };
+        auto pairfn = [&](int j, float2 s, float2 sn, float2 cs) {
+            const float2 a = fma2(sn, e2, cs);
+            const float2 b = add2(sn, cs);
+            // the residual of the group's five RN(e^2) decays goes in at position 1 (any position is equivalent to
+            // first order; ptxas' schedule of this one is 1.7 % faster than of the others, profiles/r01_ab_variants_decomposed.txt)
+            if (j == 1) st.h = fma2(st.h, splat(md.rho5), st.h);
+            st.h = fma2(s, a, mul2(st.h, ee2));
+            st.W = fma2(s, b, st.W);
+        };
+        auto pairfn1 = [&](int, float2 s, float2 sn, float2 cs) {
+            const float2 a = fma2(sn, e2, cs);
+            const float2 b = add2(sn, cs);
+            st.h = fma2(s, a, mul2(st.h, ee2));
+            st.W = fma2(s, b, st.W);
+        };
+        // n_pairs pair steps in groups of five (pairfn adds the group's decay residual), single pairs for the rest
+        auto advance = [&](int n_pairs) {
+            int k = 0;
+            for (; k + 5 <= n_pairs; k += 5) {
+                run_pairs_parts<5>(t, pair, pairfn);
+                pair += 5;
+            }
+            for (; k < n_pairs; ++k) {
+                st.h = fma2(st.h, splat(md.rho1), st.h);
+                run_pairs_parts<1>(t, pair, pairfn1);
+                pair += 1;
+            }
+        };
 
         auto save_curve = [&](int m) {
-            const float2 q = st.q();
 #pragma unroll
             for (int s = 0; s < NCUR; ++s) {
                 // p0 = e^{-I+} + e^{-I-} = e^{-Im} (e^{-c q} + e^{+c q});  centred: d = p0 - 2 e^{-Im}
@@ -143,7 +182,8 @@ fast_kernel(StreamGeom g, SeedArgs seeds, ModelDev md, FastScen cs0, FastScen cs
                 // truncation < 3e-8 relative for |z| <= 1.2 (z is the noise part of the integral, sd 0.29 at T = 10),
                 // no cancellation at short maturities, and no XU work; a warp holding a |z| > 1.2 (0.3 % of the
                 // warps at the last maturity) takes the exponential form
-                const float2 z = mul2(q, splat(s ? cs1.c : cs0.c));
+                // z = c q = (c qA) W - (c qB) h
+                const float2 z = fma2(st.W, splat(s ? zA1 : zA0), mul2(st.h, splat(s ? zB1 : zB0)));
                 float2 d2;
                 if (__any_sync(0xffffffffu, fmaxf(fabsf(z.x), fabsf(z.y)) > 1.2f)) {
                     const float2 y = mul2(z, splat(kLog2e));
@@ -160,7 +200,7 @@ fast_kernel(StreamGeom g, SeedArgs seeds, ModelDev md, FastScen cs0, FastScen cs
                 }
                 float2 dv = mul2(d2, splat(emI[s * n_mat + m]));
 #else
-                const float2 y = mul2(q, splat(s ? kc1 : kc0));
+                const float2 y = mul2(st.q(md.qA, md.qB), splat(s ? kc1 : kc0));
                 const float2 ep = make_float2(mufu_ex2(y.x), mufu_ex2(y.y));
                 const float2 en = make_float2(mufu_ex2(-y.x), mufu_ex2(-y.y));
                 float2 dv = mul2(add2(add2(ep, en), splat(-2.0f)), splat(emI[s * n_mat + m]));
@@ -172,7 +212,7 @@ fast_kernel(StreamGeom g, SeedArgs seeds, ModelDev md, FastScen cs0, FastScen cs
         };
 
         auto eval_S1 = [&]() {
-            const float2 q = st.q();
+            const float2 q = st.q(md.qA, md.qB);
             const double mA = t.validA ? 1.0 : 0.0, mB = t.validB ? 1.0 : 0.0;
 #pragma unroll
             for (int s = 0; s < NZBC; ++s) {
@@ -224,15 +264,14 @@ fast_kernel(StreamGeom g, SeedArgs seeds, ModelDev md, FastScen cs0, FastScen cs
             }
         };
 
-        int pair = 0;
         if (NCUR) {
             for (int m = 1; m < n_mat; ++m) {
-                advance_pairs(t, pair, half, pairfn);
+                advance(half);
                 save_curve(m);
                 if (kS1 > 0 && m == m_S1) eval_S1();
                 if (DUMP && m == m_S1) {
                     float2* d = dump + ((size_t)run * g.n_chunks + chunk) * kChunk + tid;
-                    const float2 q = st.q();
+                    const float2 q = st.q(md.qA, md.qB);
                     d[0] = make_float2(st.h.x, q.x);
                     d[kThreads] = make_float2(st.h.y, q.y);
                 }
@@ -244,7 +283,7 @@ fast_kernel(StreamGeom g, SeedArgs seeds, ModelDev md, FastScen cs0, FastScen cs
                 one_pair(t, ns, nc);
                 step1(nc);
             }
-            advance_pairs(t, pair, n_main >> 1, pairfn);
+            advance(n_main >> 1);
             if (n_main & 1) {            // odd tail: sin branch only
                 float2 ns, nc;
                 one_pair(t, ns, nc);
