@@ -224,6 +224,37 @@ def test_finish_beyond_int_range(engine, hw, curve):
     assert z["price_cv"] == big["zbc"]["price_cv"]
 
 
+def test_host_side_caches_follow_the_model(hw, curve):
+    """the engine caches host-built tables (model arena, bumped-sigma FD arena) and the (int)(S1/dt) probe; every
+    cache must be invalidated by a model change and keyed by its own arguments"""
+    eng = hw.Engine(device=0)
+    try:
+        assert eng.steps_to(5.0) == 500 and eng.steps_to(5.0) == 500 and eng.steps_to(2.5) == 250
+        fd1 = eng.vega_fd(hw.Rng(SEED, N), curve["P"], curve["f"], eps=0.001, n_steps_S1=500)
+        fd2 = eng.vega_fd(hw.Rng(SEED, N), curve["P"], curve["f"], eps=0.002, n_steps_S1=500)
+        fd1b = eng.vega_fd(hw.Rng(SEED, N), curve["P"], curve["f"], eps=0.001, n_steps_S1=500)
+        assert fd1["price_minus"] == fd1b["price_minus"] and fd1["price_plus"] == fd1b["price_plus"]
+        assert fd2["price_minus"] < fd1["price_minus"] < fd1["price_plus"] < fd2["price_plus"]
+        # another model on the same engine: shorter grid, other sigma
+        eng.set_model(hw.default_params(n_steps=200, n_mat=21, sigma=0.15))
+        assert eng.steps_to(5.0) == 100
+        c2 = eng.bond_curve(hw.Rng(SEED, N))
+        fresh = hw.Engine(device=0, params=hw.default_params(n_steps=200, n_mat=21, sigma=0.15))
+        c2f = fresh.bond_curve(hw.Rng(SEED, N))
+        assert (c2["P"] == c2f["P"]).all()
+        a = eng.vega_fd(hw.Rng(SEED, N), c2["P"], c2["f"], eps=0.001, n_steps_S1=100)
+        b = fresh.vega_fd(hw.Rng(SEED, N), c2f["P"], c2f["f"], eps=0.001, n_steps_S1=100)
+        assert a["price_minus"] == b["price_minus"] and a["price_plus"] == b["price_plus"]
+        fresh.close()
+        # and back: the default model's results are reproduced bit for bit
+        eng.set_model(hw.default_params())
+        assert eng.steps_to(5.0) == 500
+        again = eng.vega_fd(hw.Rng(SEED, N), curve["P"], curve["f"], eps=0.001, n_steps_S1=500)
+        assert again["price_minus"] == fd1["price_minus"] and again["price_plus"] == fd1["price_plus"]
+    finally:
+        eng.close()
+
+
 def test_engine_lifecycle_and_argument_errors(hw, curve):
     """create/destroy repeatedly, bad arguments come back as status codes, never as a crash or exit()"""
     import ctypes as C
