@@ -298,6 +298,8 @@ def test_grid_stride_chunks_large_run(engine, hw, curve):
     dict(n_steps=400, n_mat=101),                                  # stride 4: remainder pairs in the 5-pair unroll
     dict(n_steps=600, n_mat=51, T_final=6.0),                      # stride 12, dt = 0.01, spacing 0.12
     dict(a=0.5, sigma=0.2, r0=0.03, theta_a0=0.02, theta_b0=0.001, theta_a1=0.03, theta_b1=-0.0005, theta_break=4.0),
+    # weak mean reversion: 1 - e^{-a dt} = 5e-4, the decomposed kernels' q = qA W - qB h has qA = 4000
+    dict(a=0.05, sigma=0.02, r0=0.02),
 ])
 @pytest.mark.parametrize("mode", [0, 1])
 def test_other_model_parameters(hw, over, mode):
