@@ -364,6 +364,13 @@ def main():
         "probes_Ginstr_s": {"ffma": ffma / 1e9, "ffma2": ffma2 / 1e9, "mufu_ex2": mufu / 1e9, "lop3_shf": alu / 1e9,
                             "i2fp": i2f / 1e9, "hw1f_mix": mix / 1e9},
         "algorithmic_per_path_step": algo,
+        # static, from the committed ncu --set full capture of this kernel (not measured in this run): the dispatch
+        # port is the binding resource -- packed FP32x2 instructions hold it for two cycles, so its utilisation is
+        # issue-active + (fma-pipe cycles - fma instructions)
+        "ncu_capture": ({"file": "profiles/r01_ncu_full_fast_kernel_v3.csv", "kernel_us": 572.7, "issue_active_pct": 81.2,
+                         "dispatch_port_pct": 94.0, "xu_pipe_pct": 80.7, "alu_pipe_pct": 65.6, "fma_pipe_cycles_pct": 43.5,
+                         "top_stall": "not_selected"} if args.mode == "decomposed" else
+                        {"file": "profiles/r01_ncu_full_bond_curve_v3.csv"}),
         "kernel": ("fast_kernel<1,0,0>" if args.mode == "decomposed" else "bond_curve_kernel<1>") +
                   " (prep_lo_kernel + reduce_curve_kernel included in the time)",
         "other_mode": {"mode": other, "ms_per_step": other_ms,
