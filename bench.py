@@ -109,7 +109,8 @@ def run_reference_arm(args, rank, real_stdout):
             "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": "Q1 bond curve: 2^20 subsequences x 2 antithetic x 1000 steps (reference "
-                                   "simulate_zcb), seeds pinned"}}
+                                   "simulate_zcb), seeds pinned",
+                       "parallelism": "single GPU on rank 0 (the reference has no multi-GPU path)"}}
     if os.path.exists(harness):
         out = os.path.join(ROOT, "gpurun_out", "ref_bench_q1.json")
         os.makedirs(os.path.dirname(out), exist_ok=True)
