@@ -443,7 +443,8 @@ int resolve_steps(hw1f_engine* e, float S1, int32_t n_in, int32_t* n_out)
     return HW1F_OK;
 }
 
-// bond plans for up to two scenarios; market set s at d_mkt[2s], d_mkt[2s+1]
+// bond plans for up to two scenarios on DEVICE-resident market curves (the recalibrated FD's own curves);
+// market set s at d_mkt[2s], d_mkt[2s+1]
 int launch_plans(hw1f_engine* e, const ScenDev* sc, int n_scen, float S1, float S2)
 {
     const int n = e->p.n_mat;
@@ -453,21 +454,33 @@ int launch_plans(hw1f_engine* e, const ScenDev* sc, int n_scen, float S1, float 
     const float* P1 = P0 + 2 * n;
     const float* f1 = P0 + 3 * n;
     bond_plan_kernel<<<1, 32, 0, e->stream>>>(model_dev(e), sc[0], sc[n_scen > 1 ? 1 : 0], n_scen, S1, S2, P0, f0,
-                                              n_scen > 1 ? P1 : P0, n_scen > 1 ? f1 : f0, e->d_plans.p);
+                                              n_scen > 1 ? P1 : P0, n_scen > 1 ? f1 : f0, e->d_plans.p, MktPts{}, 0);
     return check_launch(e, "bond_plan_kernel");
 }
 
-// market set `set` (0 or 1) <- (P_mkt, f_mkt); both = true fills sets 0 AND 1 with the same curves in one copy
-int upload_market(hw1f_engine* e, int set, const float* P_mkt, const float* f_mkt, bool both = false)
+// bond plans for one or two scenarios priced on HOST-resident market curves: the six values the plan reads travel
+// as kernel arguments -- no market upload, one launch.  Plans go to d_plans[slot0 ..).
+int launch_plans_host(hw1f_engine* e, const ScenDev* sc, int n_scen, float S1, float S2, const float* P_mkt,
+                      const float* f_mkt, int slot0 = 0)
 {
     const int n = e->p.n_mat;
-    HW_CUDA(e, e->d_mkt.ensure(4 * (size_t)n));
-    std::vector<float> tmp((both ? 4 : 2) * (size_t)n);
-    for (int k = 0; k < (both ? 2 : 1); ++k) {
-        memcpy(tmp.data() + 2 * (size_t)k * n, P_mkt, n * sizeof(float));
-        memcpy(tmp.data() + 2 * (size_t)k * n + n, f_mkt, n * sizeof(float));
-    }
-    return upload(e, e->d_mkt.p + (both ? 0 : 2 * (size_t)set * n), tmp.data(), tmp.size() * sizeof(float));
+    HW_CUDA(e, e->d_plans.ensure(4));
+    const ModelDev md = model_dev(e);
+    MktPts pts{};
+    auto pick = [&](const float* data, float T, float out[2]) {
+        const float prod = T * md.inv_spacing;           // IEEE single multiply, like mul_() on the device
+        int idx = (prod >= (float)n) ? n : (int)prod;    // (int): truncation = __float2int_rz
+        if (idx < 0) idx = 0;
+        if (idx >= n - 1) { out[0] = data[n - 1]; out[1] = data[n - 1]; }
+        else { out[0] = data[idx]; out[1] = data[idx + 1]; }
+        return idx;
+    };
+    pts.idx_S2 = pick(P_mkt, S2, pts.P_S2);
+    pts.idx_S1 = pick(P_mkt, S1, pts.P_S1);
+    pick(f_mkt, S1, pts.f_S1);
+    bond_plan_kernel<<<1, 32, 0, e->stream>>>(md, sc[0], sc[n_scen > 1 ? 1 : 0], n_scen, S1, S2, nullptr, nullptr, nullptr,
+                                              nullptr, e->d_plans.p + slot0, pts, 1);
+    return check_launch(e, "bond_plan_kernel");
 }
 
 ScenDev scen_dev(const hw1f_engine* e, float sigma, float sig_st, int drift_slot)
@@ -1169,11 +1182,10 @@ int hw1f_zbc_cv_moments(hw1f_engine* e, hw1f_rng* rng, float S1, float S2, float
     HW_CUDA(e, cudaSetDevice(e->device));
     int32_t n = 0;
     HW_TRY(resolve_steps(e, S1, n_steps_S1, &n));
-    HW_TRY(upload_market(e, 0, P_mkt, f_mkt));
     const ScenDev sc = scen_dev(e, e->p.sigma, e->sig_st, 0);
-    HW_TRY(launch_plans(e, &sc, 1, S1, S2));
-    Launch L;
+    Launch L;   // the per-launch jump table first: the plan launch is enqueued while it runs
     HW_TRY(prepare_launch(e, &rng->seed, 1, rng->first_path, rng->n_paths, rng->offset, &L));
+    HW_TRY(launch_plans_host(e, &sc, 1, S1, S2, P_mkt, f_mkt));
     HW_TRY(launch_zbc(e, L, &sc, 1, n, K, d_moments));
     rng->offset += (uint64_t)n;
     return HW1F_OK;
@@ -1223,9 +1235,8 @@ int hw1f_zbc_cv_batch(hw1f_engine* e, const uint64_t* seeds, int32_t n_runs, uin
     int32_t n = 0;
     HW_TRY(resolve_steps(e, S1, n_steps_S1, &n));
     HW_CUDA(e, e->d_moments.ensure(4 * (size_t)e->p.n_mat * kMaxRuns));
-    HW_TRY(upload_market(e, 0, P_mkt, f_mkt));
     const ScenDev sc = scen_dev(e, e->p.sigma, e->sig_st, 0);
-    HW_TRY(launch_plans(e, &sc, 1, S1, S2));
+    HW_TRY(launch_plans_host(e, &sc, 1, S1, S2, P_mkt, f_mkt));
     {
         const hw1f_rng geom{0, 0, n_paths, 0};
         HW_TRY(warm_geometry(e, &geom));
@@ -1255,11 +1266,10 @@ int hw1f_vega_pathwise_moments(hw1f_engine* e, hw1f_rng* rng, float S1, float S2
     HW_CUDA(e, cudaSetDevice(e->device));
     int32_t n = 0;
     HW_TRY(resolve_steps(e, S1, n_steps_S1, &n));
-    HW_TRY(upload_market(e, 0, P_mkt, f_mkt));
     const ScenDev sc = scen_dev(e, e->p.sigma, e->sig_st, 0);
-    HW_TRY(launch_plans(e, &sc, 1, S1, S2));
-    Launch L;
+    Launch L;   // the per-launch jump table first: the plan launch is enqueued while it runs
     HW_TRY(prepare_launch(e, &rng->seed, 1, rng->first_path, rng->n_paths, rng->offset, &L));
+    HW_TRY(launch_plans_host(e, &sc, 1, S1, S2, P_mkt, f_mkt));
     HW_TRY(launch_pathwise(e, L, sc, n, K, d_moments));
     rng->offset += (uint64_t)n;
     return HW1F_OK;
@@ -1300,9 +1310,8 @@ int hw1f_vega_pathwise_batch(hw1f_engine* e, const uint64_t* seeds, int32_t n_ru
     int32_t n = 0;
     HW_TRY(resolve_steps(e, S1, n_steps_S1, &n));
     HW_CUDA(e, e->d_moments.ensure(4 * (size_t)e->p.n_mat * kMaxRuns));
-    HW_TRY(upload_market(e, 0, P_mkt, f_mkt));
     const ScenDev sc = scen_dev(e, e->p.sigma, e->sig_st, 0);
-    HW_TRY(launch_plans(e, &sc, 1, S1, S2));
+    HW_TRY(launch_plans_host(e, &sc, 1, S1, S2, P_mkt, f_mkt));
     {
         const hw1f_rng geom{0, 0, n_paths, 0};
         HW_TRY(warm_geometry(e, &geom));
@@ -1345,13 +1354,12 @@ int hw1f_vega_fd(hw1f_engine* e, hw1f_rng* rng, float S1, float S2, float K, con
     // both bumps read the same market curves and the same normals
     const float sig_m = e->p.sigma - eps, sig_p = e->p.sigma + eps;
     HW_TRY(upload_fd_tables(e, sig_m, sig_p));
-    HW_TRY(upload_market(e, 0, P_mkt, f_mkt, true));
     ScenDev sc[2] = {scen_dev(e, sig_m, host_sig_st(e->p, sig_m), 2), scen_dev(e, sig_p, host_sig_st(e->p, sig_p), 3)};
     HW_TRY(warm_geometry(e, rng));
     HW_CUDA(e, cudaEventRecord(e->ev0, e->stream));
-    HW_TRY(launch_plans(e, sc, 2, S1, S2));
     Launch L;
     HW_TRY(prepare_launch(e, &rng->seed, 1, rng->first_path, rng->n_paths, rng->offset, &L));
+    HW_TRY(launch_plans_host(e, sc, 2, S1, S2, P_mkt, f_mkt));
     HW_TRY(launch_zbc(e, L, sc, 2, n, K, e->d_moments.p));
     HW_CUDA(e, cudaEventRecord(e->ev1, e->stream));
     double mom[10];
@@ -1449,25 +1457,19 @@ static int fused_launch(hw1f_engine* e, hw1f_rng* rng, float S1, float S2, float
         e->err = "fused pass needs an even normal offset, an even save stride and n_steps_S1 on the maturity grid";
         return HW1F_ERR_UNSUPPORTED;
     }
-    HW_TRY(upload_market(e, 0, P_mkt, f_mkt));
     ScenDev sc[3] = {scen_dev(e, e->p.sigma, e->sig_st, 0), scen_dev(e, e->p.sigma, e->sig_st, 0),
                      scen_dev(e, e->p.sigma, e->sig_st, 0)};
-    HW_CUDA(e, e->d_plans.ensure(4));
-    HW_TRY(launch_plans(e, sc, 1, S1, S2));
     if (fd) {   // run_finite_difference's scenarios (src/3:414-435): sigma -/+ eps, shifted drift, same curves
         const float sig_m = e->p.sigma - eps, sig_p = e->p.sigma + eps;
         HW_TRY(upload_fd_tables(e, sig_m, sig_p));
-        HW_TRY(upload_market(e, 1, P_mkt, f_mkt));
         sc[1] = scen_dev(e, sig_m, host_sig_st(e->p, sig_m), 2);
         sc[2] = scen_dev(e, sig_p, host_sig_st(e->p, sig_p), 3);
-        const int nmk = e->p.n_mat;
-        const float* P0 = e->d_mkt.p;
-        bond_plan_kernel<<<1, 32, 0, e->stream>>>(model_dev(e), sc[1], sc[2], 2, S1, S2, P0, P0 + nmk, P0 + 2 * nmk,
-                                                  P0 + 3 * nmk, e->d_plans.p + 1);
-        HW_TRY(check_launch(e, "bond_plan_kernel"));
     }
+    // the per-launch jump table first: the plan launches are enqueued while it runs
     Launch L;
     HW_TRY(prepare_launch(e, &rng->seed, 1, rng->first_path, rng->n_paths, rng->offset, &L));
+    HW_TRY(launch_plans_host(e, sc, 1, S1, S2, P_mkt, f_mkt, 0));
+    if (fd) HW_TRY(launch_plans_host(e, sc + 1, 2, S1, S2, P_mkt, f_mkt, 1));
     const int nm = e->p.n_mat, next = kFusedExtra + (fd ? kFusedFdExtra : 0), nq = 2 * nm + next;
     HW_CUDA(e, e->d_partials.ensure((size_t)L.grid_x * nq));
     if (e->mode == HW1F_MODE_DECOMPOSED) {
@@ -1656,9 +1658,8 @@ int hw1f_reduction_bench(hw1f_engine* e, hw1f_rng* rng, int32_t method, float S1
     HW_CUDA(e, cudaSetDevice(e->device));
     int32_t n = 0;
     HW_TRY(resolve_steps(e, S1, n_steps_S1, &n));
-    HW_TRY(upload_market(e, 0, P_mkt, f_mkt));
     const ScenDev sc = scen_dev(e, e->p.sigma, e->sig_st, 0);
-    HW_TRY(launch_plans(e, &sc, 1, S1, S2));
+    HW_TRY(launch_plans_host(e, &sc, 1, S1, S2, P_mkt, f_mkt));
     HW_CUDA(e, e->d_moments.ensure(4 * (size_t)e->p.n_mat * kMaxRuns));
     HW_CUDA(e, e->d_out.ensure(64));
     float* d_sum = e->d_out.p;

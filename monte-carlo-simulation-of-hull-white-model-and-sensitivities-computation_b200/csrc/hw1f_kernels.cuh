@@ -102,20 +102,33 @@ prep_lo_kernel(SeedArgs seeds, int n_runs, uint32_t L_log2, const uint32_t* __re
     }
 }
 
-__device__ __forceinline__ float interp_mkt(const float* __restrict__ data, float T, const ModelDev& md)
+// interpolate() of common.cuh:187-196 as compiled: T/spacing -> T*10, alpha via one FFMA.  d0 = data[idx],
+// d1 = data[idx+1]; idx >= n_mat-1 returns d0 (= data[n_mat-1])
+__device__ __forceinline__ float interp_pts(float d0, float d1, int idx, float T, const ModelDev& md)
 {
-    // interpolate() of common.cuh:187-196 as compiled: T/spacing -> T*10, alpha via one FFMA
-    const int idx = __float2int_rz(mul_(T, md.inv_spacing));
-    if (idx >= md.n_mat - 1) return data[md.n_mat - 1];
+    if (idx >= md.n_mat - 1) return d0;
     const float al = mul_(fma_(__int2float_rn(idx), md.neg_spacing, T), md.inv_spacing);
     const float om = sub_(1.0f, al);
-    return fma_(data[idx], om, mul_(al, data[idx + 1]));
+    return fma_(d0, om, mul_(al, d1));
 }
+__device__ __forceinline__ float interp_mkt(const float* __restrict__ data, float T, const ModelDev& md)
+{
+    const int idx = __float2int_rz(mul_(T, md.inv_spacing));
+    if (idx >= md.n_mat - 1) return data[md.n_mat - 1];
+    return interp_pts(data[idx], data[idx + 1], idx, T, md);
+}
+
+// the six market values a bond plan reads, picked on the host (the grid index (int)(T * inv_spacing) is plain
+// IEEE arithmetic); the interpolation itself and everything after it stays on the device
+struct MktPts {
+    float P_S2[2], P_S1[2], f_S1[2];   // data[idx], data[idx+1] around S2 (P) and S1 (P, f)
+    int idx_S2, idx_S1;
+};
 
 __global__ void bond_plan_kernel(ModelDev md, ScenDev sc0, ScenDev sc1, int n_scen, float S1, float S2,
                                  const float* __restrict__ P_mkt0, const float* __restrict__ f_mkt0,
                                  const float* __restrict__ P_mkt1, const float* __restrict__ f_mkt1,
-                                 BondPlan* __restrict__ plans)
+                                 BondPlan* __restrict__ plans, MktPts pts, int use_pts)
 {
     const int s = threadIdx.x;
     if (s >= n_scen) return;
@@ -124,9 +137,10 @@ __global__ void bond_plan_kernel(ModelDev md, ScenDev sc0, ScenDev sc1, int n_sc
     const float* f_mkt = s ? f_mkt1 : f_mkt0;
     const float a = md.a, sigma = sc.sigma;
     const float B = mul_(sub_(1.0f, mufu_ex2(mul_(mul_(sub_(S2, S1), a), -kLog2e))), mufu_rcp(a));
-    const float P0T = interp_mkt(P_mkt, S2, md);
-    const float P0t = interp_mkt(P_mkt, S1, md);
-    const float f0t = interp_mkt(f_mkt, S1, md);
+    // use_pts: host-resident market curves (every scenario prices on the same curves); else device curves
+    const float P0T = use_pts ? interp_pts(pts.P_S2[0], pts.P_S2[1], pts.idx_S2, S2, md) : interp_mkt(P_mkt, S2, md);
+    const float P0t = use_pts ? interp_pts(pts.P_S1[0], pts.P_S1[1], pts.idx_S1, S1, md) : interp_mkt(P_mkt, S1, md);
+    const float f0t = use_pts ? interp_pts(pts.f_S1[0], pts.f_S1[1], pts.idx_S1, S1, md) : interp_mkt(f_mkt, S1, md);
     const float om2 = sub_(1.0f, mufu_ex2(mul_(mul_(mul_(a, -2.0f), S1), kLog2e)));
     float t3 = mul_(mul_(mul_(sigma, sigma), mufu_rcp(mul_(a, 4.0f))), om2);
     t3 = mul_(t3, B);
