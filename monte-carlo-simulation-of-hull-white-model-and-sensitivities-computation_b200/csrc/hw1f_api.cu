@@ -1404,7 +1404,9 @@ int hw1f_vega_fd_recalibrated(hw1f_engine* e, hw1f_rng* rng, float S1, float S2,
     // decomposed mode, S1 on the maturity grid: the curve pass parks every subsequence's noise state at step n, and
     // the two prices are evaluated from it once the recalibrated curves exist -- normals [off, off+n) are the first
     // n normals of the curve window, so nothing is simulated twice.  Otherwise: second pass over [off, off+n).
-    const bool one_pass = e->mode == HW1F_MODE_DECOMPOSED && n > 0 && (n % e->stride) == 0;
+    // (8 bytes of parked state per subsequence: above 2^27 subsequences = 1 GB the second pass is used instead)
+    const bool one_pass = e->mode == HW1F_MODE_DECOMPOSED && n > 0 && (n % e->stride) == 0 &&
+                          rng->n_paths <= (1ull << 27);
     HW_TRY(launch_curve(e, L, sc, 2, e->d_moments.p, one_pass ? n : 0));
     const float inv_dT = 1.0f / e->spacing;
     for (int s = 0; s < 2; ++s) {
