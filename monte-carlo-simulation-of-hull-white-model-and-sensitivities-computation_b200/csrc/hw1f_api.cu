@@ -60,7 +60,7 @@ struct hw1f_engine {
     int sm_count = 148;
     size_t smem_optin = 0;
     cudaStream_t stream = nullptr, own_stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_stage = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr, ev_stage = nullptr;
     std::string err = "";
     uint64_t launches = 0;
 
@@ -845,6 +845,7 @@ int hw1f_engine_create(int device, hw1f_engine** out)
     e->smem_optin = prop.sharedMemPerBlockOptin;
     if (cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreate(&e->ev0) != cudaSuccess || cudaEventCreate(&e->ev1) != cudaSuccess ||
+        cudaEventCreate(&e->ev2) != cudaSuccess || cudaEventCreate(&e->ev3) != cudaSuccess ||
         cudaEventCreateWithFlags(&e->ev_stage, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&e->ev_model, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&e->ev_fd, cudaEventDisableTiming) != cudaSuccess) {
@@ -880,6 +881,8 @@ int hw1f_engine_destroy(hw1f_engine* e)
     if (e->h_stage) cudaFreeHost(e->h_stage);
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
+    if (e->ev2) cudaEventDestroy(e->ev2);
+    if (e->ev3) cudaEventDestroy(e->ev3);
     if (e->ev_stage) cudaEventDestroy(e->ev_stage);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
     delete e;
@@ -1437,13 +1440,94 @@ int hw1f_vega(hw1f_engine* e, hw1f_rng* rng, float S1, float S2, float K, const 
               float eps, int32_t n_steps_S1, hw1f_vega_result* out)
 {
     HW_TRY(require_model(e));
-    if (!rng || !out) return HW1F_ERR_INVALID;
+    if (!rng || !out || !P_mkt || !f_mkt) return HW1F_ERR_INVALID;
+    HW_REQUIRE(e, 2 * rng->n_paths < (1ull << 31), "the reference's int N_total needs 2*n_paths < 2^31");
+    HW_CUDA(e, cudaSetDevice(e->device));
     memset(out, 0, sizeof(*out));
     int32_t n = 0;
     HW_TRY(resolve_steps(e, S1, n_steps_S1, &n));
-    HW_TRY(hw1f_vega_pathwise(e, rng, S1, S2, K, P_mkt, f_mkt, n, out));     // normals [0,n)
-    HW_TRY(hw1f_vega_fd(e, rng, S1, S2, K, P_mkt, f_mkt, eps, n, out));      // normals [n,2n)
-    HW_TRY(hw1f_vega_fd_recalibrated(e, rng, S1, S2, K, eps, n, out));       // normals [2n,..)
+    const int nm = e->p.n_mat;
+    if ((rng->offset & 1) || (e->stride & 1)) {
+        // the recalibration window [off+2n, ..) must start on a Box-Muller pair boundary: take the three calls, whose
+        // own checks report what is unsupported
+        HW_TRY(hw1f_vega_pathwise(e, rng, S1, S2, K, P_mkt, f_mkt, n, out));     // normals [0,n)
+        HW_TRY(hw1f_vega_fd(e, rng, S1, S2, K, P_mkt, f_mkt, eps, n, out));      // normals [n,2n)
+        return hw1f_vega_fd_recalibrated(e, rng, S1, S2, K, eps, n, out);        // normals [2n,..)
+    }
+    // The three estimators of the reference's main() (src/3:697-834) enqueued back to back -- same launches, same draw
+    // windows and same results as hw1f_vega_pathwise + hw1f_vega_fd + hw1f_vega_fd_recalibrated -- with ONE read-back
+    // at the end instead of a host round trip after each of them.
+    HW_CUDA(e, e->d_moments.ensure(4 * (size_t)nm * kMaxRuns));
+    HW_CUDA(e, e->d_out.ensure(4 * (size_t)nm));
+    HW_CUDA(e, e->d_mkt.ensure(4 * (size_t)nm));
+    double* const res = e->d_moments.p + 4 * (size_t)nm;   // [0,2) pathwise, [8,18) FD, [24,34) recalibrated FD
+    const float sig_m = e->p.sigma - eps, sig_p = e->p.sigma + eps;
+    const ScenDev base = scen_dev(e, e->p.sigma, e->sig_st, 0);
+    ScenDev fd[2] = {scen_dev(e, sig_m, host_sig_st(e->p, sig_m), 2), scen_dev(e, sig_p, host_sig_st(e->p, sig_p), 3)};
+    ScenDev rc[2] = {scen_dev(e, sig_m, host_sig_st(e->p, sig_m), 0), scen_dev(e, sig_p, host_sig_st(e->p, sig_p), 0)};
+    HW_TRY(upload_fd_tables(e, sig_m, sig_p));
+    HW_TRY(warm_geometry(e, rng));
+    Launch L;
+    // pathwise tangent, normals [off, off+n)  (simulate_sensitivity, src/3:251)
+    HW_CUDA(e, cudaEventRecord(e->ev0, e->stream));
+    HW_TRY(prepare_launch(e, &rng->seed, 1, rng->first_path, rng->n_paths, rng->offset, &L));
+    HW_TRY(launch_plans_host(e, &base, 1, S1, S2, P_mkt, f_mkt));
+    HW_TRY(launch_pathwise(e, L, base, n, K, res));
+    rng->offset += (uint64_t)n;
+    // CRN finite differences, normals [off+n, off+2n)  (run_finite_difference, src/3:400-446)
+    HW_CUDA(e, cudaEventRecord(e->ev1, e->stream));
+    HW_TRY(prepare_launch(e, &rng->seed, 1, rng->first_path, rng->n_paths, rng->offset, &L));
+    HW_TRY(launch_plans_host(e, fd, 2, S1, S2, P_mkt, f_mkt));
+    HW_TRY(launch_zbc(e, L, fd, 2, n, K, res + 8));
+    rng->offset += (uint64_t)n;
+    // recalibrated finite differences, curves on [off+2n, off+2n+N_STEPS), prices on [off+2n, off+3n)  (src/3:449-525)
+    HW_CUDA(e, cudaEventRecord(e->ev2, e->stream));
+    HW_TRY(prepare_launch(e, &rng->seed, 1, rng->first_path, rng->n_paths, rng->offset, &L));
+    const bool one_pass = e->mode == HW1F_MODE_DECOMPOSED && n > 0 && (n % e->stride) == 0 &&
+                          rng->n_paths <= (1ull << 27);
+    HW_TRY(launch_curve(e, L, rc, 2, e->d_moments.p, one_pass ? n : 0));
+    const float inv_dT = 1.0f / e->spacing;
+    for (int s = 0; s < 2; ++s) {
+        float* dP = e->d_mkt.p + 2 * (size_t)s * nm;
+        curve_epilogue_kernel<<<1, ((nm + 31) / 32) * 32, nm * sizeof(float), e->stream>>>(
+            e->d_moments.p + 2 * (size_t)s * nm, nm, rng->n_paths, inv_dT, dP, dP + nm, nullptr);
+        HW_TRY(check_launch(e, "curve_epilogue_kernel"));
+    }
+    HW_TRY(launch_plans(e, rc, 2, S1, S2));
+    if (one_pass) HW_TRY(launch_zbc_from_state(e, L, rc, n, K, res + 24));
+    else HW_TRY(launch_zbc(e, L, rc, 2, n, K, res + 24));
+    rng->offset += (uint64_t)n;
+    HW_CUDA(e, cudaEventRecord(e->ev3, e->stream));
+    // one read-back: 34 doubles of moments and P(0, T_final) of both recalibrated curves
+    HW_CUDA(e, cudaEventSynchronize(e->ev_stage));
+    HW_TRY(stage_reserve(e, 34 * sizeof(double) + 2 * sizeof(float)));
+    char* hs = static_cast<char*>(e->h_stage);
+    HW_CUDA(e, cudaMemcpyAsync(hs, res, 34 * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    for (int s = 0; s < 2; ++s)
+        HW_CUDA(e, cudaMemcpyAsync(hs + 34 * sizeof(double) + s * sizeof(float),
+                                   e->d_mkt.p + 2 * (size_t)s * nm + (nm - 1), sizeof(float), cudaMemcpyDeviceToHost,
+                                   e->stream));
+    HW_CUDA(e, cudaStreamSynchronize(e->stream));
+    double mom[34];
+    float P0S2_rc[2];
+    memcpy(mom, hs, sizeof(mom));
+    memcpy(P0S2_rc, hs + sizeof(mom), sizeof(P0S2_rc));
+    const double np = (double)rng->n_paths;
+    const float P0S2 = P_mkt[nm - 1];
+    out->n_steps_S1 = n;
+    out->vega_pathwise = (float)mom[0] / (float)(int)rng->n_paths;   // sum / N_PATHS in float, src/3:261
+    out->vega_pathwise_f64 = mom[0] / np;
+    const double var = (np > 1) ? (mom[1] - mom[0] * mom[0] / np) / (np - 1.0) : 0.0;
+    out->vega_pathwise_se = (var > 0) ? sqrt(var / np) : 0.0;
+    out->price_minus = zbc_price_cv(mom + 8, rng->n_paths, P0S2);
+    out->price_plus = zbc_price_cv(mom + 13, rng->n_paths, P0S2);
+    out->vega_fd = (out->price_plus - out->price_minus) / (2.0f * eps);                     // src/3:443
+    out->price_minus_recal = zbc_price_cv(mom + 24, rng->n_paths, P0S2_rc[0]);
+    out->price_plus_recal = zbc_price_cv(mom + 29, rng->n_paths, P0S2_rc[1]);
+    out->vega_fd_recal = (out->price_plus_recal - out->price_minus_recal) / (2.0f * eps);   // src/3:513
+    HW_CUDA(e, cudaEventElapsedTime(&out->ms_pathwise, e->ev0, e->ev1));
+    HW_CUDA(e, cudaEventElapsedTime(&out->ms_fd, e->ev1, e->ev2));
+    HW_CUDA(e, cudaEventElapsedTime(&out->ms_fd_recal, e->ev2, e->ev3));
     return HW1F_OK;
 }
 
