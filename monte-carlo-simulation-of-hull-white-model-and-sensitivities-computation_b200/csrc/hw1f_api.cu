@@ -1622,11 +1622,27 @@ int hw1f_fused_finish(hw1f_engine* e, const double* d_moments, uint64_t n_paths_
     HW_TRY(require_model(e));
     if (!d_moments || !P || !f || !zbc || !vega) return HW1F_ERR_INVALID;
     HW_CUDA(e, cudaSetDevice(e->device));
+    HW_REQUIRE(e, n_paths_total >= 1 && n_paths_total < (1ull << 40), "n_paths_total outside [1, 2^40)");
     const bool fd = eps > 0.0f;
     const int nm = e->p.n_mat, next = kFusedExtra + (fd ? kFusedFdExtra : 0);
-    HW_TRY(hw1f_bond_curve_finish(e, d_moments, n_paths_total, P, f, P_se));
+    // curve epilogue on the device, then ONE read-back of (P, f, P_se) and the S1 block of the moment vector
+    HW_CUDA(e, e->d_out.ensure(4 * (size_t)nm));
+    float* dP = e->d_out.p;
+    curve_epilogue_kernel<<<1, ((nm + 31) / 32) * 32, nm * sizeof(float), e->stream>>>(
+        d_moments, nm, n_paths_total, 1.0f / e->spacing, dP, dP + nm, dP + 2 * nm);
+    HW_TRY(check_launch(e, "curve_epilogue_kernel"));
+    const size_t bytes_ext = (size_t)next * sizeof(double), bytes_cur = 3 * (size_t)nm * sizeof(float);
+    HW_CUDA(e, cudaEventSynchronize(e->ev_stage));
+    HW_TRY(stage_reserve(e, bytes_ext + bytes_cur));
+    char* hs = static_cast<char*>(e->h_stage);
+    HW_CUDA(e, cudaMemcpyAsync(hs, d_moments + 2 * nm, bytes_ext, cudaMemcpyDeviceToHost, e->stream));
+    HW_CUDA(e, cudaMemcpyAsync(hs + bytes_ext, dP, bytes_cur, cudaMemcpyDeviceToHost, e->stream));
+    HW_CUDA(e, cudaStreamSynchronize(e->stream));
     std::vector<double> ext(next);
-    HW_TRY(download(e, ext.data(), d_moments + 2 * nm, ext.size() * sizeof(double)));
+    memcpy(ext.data(), hs, bytes_ext);
+    memcpy(P, hs + bytes_ext, nm * sizeof(float));
+    memcpy(f, hs + bytes_ext + nm * sizeof(float), nm * sizeof(float));
+    if (P_se) memcpy(P_se, hs + bytes_ext + 2 * nm * sizeof(float), nm * sizeof(float));
     zbc_algebra(ext.data(), n_paths_total, P0S2, n_steps_S1, zbc);
     memset(vega, 0, sizeof(*vega));
     vega->n_steps_S1 = n_steps_S1;
