@@ -99,7 +99,6 @@ struct hw1f_engine {
     size_t model_bytes = 0;
     bool model_cached = false;
     hw1f_params cached_p{};
-    cudaEvent_t ev_model = nullptr;
     // FD arena: shifted drift tables and exp(-Im) of the sigma -/+ eps scenarios (slots 2, 3) in one device
     // allocation with a pinned host mirror; rebuilt on the host only when (model, sigma pair) changes,
     // uploaded with ONE copy per pricing call (the reference re-sends the tables per bump, src/3:416-441)
@@ -847,7 +846,6 @@ int hw1f_engine_create(int device, hw1f_engine** out)
         cudaEventCreate(&e->ev0) != cudaSuccess || cudaEventCreate(&e->ev1) != cudaSuccess ||
         cudaEventCreate(&e->ev2) != cudaSuccess || cudaEventCreate(&e->ev3) != cudaSuccess ||
         cudaEventCreateWithFlags(&e->ev_stage, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&e->ev_model, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&e->ev_fd, cudaEventDisableTiming) != cudaSuccess) {
         delete e;
         return HW1F_ERR_CUDA;
@@ -876,7 +874,6 @@ int hw1f_engine_destroy(hw1f_engine* e)
     e->d_fd.release();
     if (e->h_model) cudaFreeHost(e->h_model);
     if (e->h_fd) cudaFreeHost(e->h_fd);
-    if (e->ev_model) cudaEventDestroy(e->ev_model);
     if (e->ev_fd) cudaEventDestroy(e->ev_fd);
     if (e->h_stage) cudaFreeHost(e->h_stage);
     if (e->ev0) cudaEventDestroy(e->ev0);
@@ -957,8 +954,8 @@ int hw1f_set_model(hw1f_engine* e, const hw1f_params* p)
     const size_t total = off_e + align((size_t)nm * sizeof(float));
     const bool same = e->model_cached && memcmp(&e->cached_p, p, sizeof(*p)) == 0 && total == e->model_bytes;
     if (!same) {
-        // a previous upload may still read the pinned mirror
-        HW_CUDA(e, cudaEventSynchronize(e->ev_model));
+        // an upload enqueued by an earlier call may still read the pinned mirror
+        HW_CUDA(e, cudaStreamSynchronize(e->stream));
         if (total != e->model_bytes) {
             HW_CUDA(e, cudaStreamSynchronize(e->stream));
             e->d_drift[0].release(); e->d_drift[1].release(); e->d_center.release(); e->d_emI[0].release();
@@ -1005,7 +1002,6 @@ int hw1f_set_model(hw1f_engine* e, const hw1f_params* p)
     // compute_constants(): ONE host->device copy of the model tables (every call, like the reference's
     // cudaMemcpyToSymbol sequence; only the host-side table building is cached)
     HW_CUDA(e, cudaMemcpyAsync(e->d_model.p, e->h_model, total, cudaMemcpyHostToDevice, e->stream));
-    HW_CUDA(e, cudaEventRecord(e->ev_model, e->stream));
     return HW1F_OK;
 }
 

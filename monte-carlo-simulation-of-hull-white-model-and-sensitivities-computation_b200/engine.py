@@ -156,11 +156,14 @@ class Engine:
     # -- model (compute_constants / compute_drift_tables, common.cuh:60-110) --
     def set_model(self, params):
         self._check(self._lib.hw1f_set_model(self._h, C.byref(params)))
+        raw = bytes(params)
+        if raw != getattr(self, "_params_raw", None):      # derived constants only change with the parameters
+            c = Constants()
+            self._check(self._lib.hw1f_get_constants(self._h, C.byref(c)))
+            self.constants = c
+            self.n_mat, self.n_steps = params.n_mat, params.n_steps
+            self._params_raw = raw
         self.params = params
-        c = Constants()
-        self._check(self._lib.hw1f_get_constants(self._h, C.byref(c)))
-        self.constants = c
-        self.n_mat, self.n_steps = params.n_mat, params.n_steps
 
     def drift_table(self, which=0, sigma=None):
         out = np.zeros(self.n_steps, np.float32)
