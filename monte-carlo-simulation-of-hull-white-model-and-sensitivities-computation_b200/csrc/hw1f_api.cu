@@ -490,6 +490,7 @@ ScenDev scen_dev(const hw1f_engine* e, float sigma, float sig_st, int drift_slot
     s.drift2 = e->d_drift[drift_slot].p;
     s.sdrift2 = e->d_drift[1].p;
     s.center = e->d_center.p;
+    s.slot = drift_slot;
     return s;
 }
 
@@ -513,12 +514,7 @@ FastTangent fast_tangent(const hw1f_engine* e, int n_steps_S1)
     return t;
 }
 
-int drift_slot_of(const hw1f_engine* e, const ScenDev& sc)
-{
-    for (int k = 0; k < 4; ++k)
-        if (sc.drift2 == e->d_drift[k].p) return k;
-    return 0;
-}
+int drift_slot_of(const hw1f_engine*, const ScenDev& sc) { return sc.slot; }
 
 size_t smem_fast(const hw1f_engine* e, int ncur)
 {
@@ -1458,10 +1454,11 @@ int hw1f_vega(hw1f_engine* e, hw1f_rng* rng, float S1, float S2, float K, const 
     HW_CUDA(e, e->d_mkt.ensure(4 * (size_t)nm));
     double* const res = e->d_moments.p + 4 * (size_t)nm;   // [0,2) pathwise, [8,18) FD, [24,34) recalibrated FD
     const float sig_m = e->p.sigma - eps, sig_p = e->p.sigma + eps;
+    // the FD arena first: scen_dev() captures the device addresses of the drift tables it names
+    HW_TRY(upload_fd_tables(e, sig_m, sig_p));
     const ScenDev base = scen_dev(e, e->p.sigma, e->sig_st, 0);
     ScenDev fd[2] = {scen_dev(e, sig_m, host_sig_st(e->p, sig_m), 2), scen_dev(e, sig_p, host_sig_st(e->p, sig_p), 3)};
     ScenDev rc[2] = {scen_dev(e, sig_m, host_sig_st(e->p, sig_m), 0), scen_dev(e, sig_p, host_sig_st(e->p, sig_p), 0)};
-    HW_TRY(upload_fd_tables(e, sig_m, sig_p));
     HW_TRY(warm_geometry(e, rng));
     Launch L;
     // pathwise tangent, normals [off, off+n)  (simulate_sensitivity, src/3:251)

@@ -64,6 +64,7 @@ struct ScenDev {
     const float2* drift2;    // duplicated (d,d) drift table in global memory
     const float2* sdrift2;   // duplicated sensitivity drift table (pathwise only)
     const float* center;     // [n_mat] centring constants c_m of the curve accumulation (Q1 only)
+    int slot;                // host bookkeeping: which of the engine's drift-table slots drift2 is
 };
 
 // path-independent pieces of P(S1,S2) = A exp(-B r) and of the pathwise tangent, computed ON

@@ -224,6 +224,51 @@ def test_finish_beyond_int_range(engine, hw, curve):
     assert z["price_cv"] == big["zbc"]["price_cv"]
 
 
+@pytest.mark.parametrize("call", ["zbc_cv", "vega_pathwise", "vega_fd", "vega_fd_recalibrated", "vega", "fused",
+                                  "zbc_cv_batch", "vega_pathwise_batch", "sample_paths", "theta"])
+def test_every_entry_point_as_first_call_of_a_fresh_engine(engine, hw, curve, call):
+    """lazily built state (jump tables, window tables, bumped-sigma arena, scratch) must not depend on what ran
+    before: each entry point, called FIRST on a new engine with a ragged path count, reproduces the long-lived
+    session engine bit for bit"""
+    n = (1 << 12) + 77
+    P, f = curve["P"], curve["f"]
+
+    def run(e):
+        if call == "zbc_cv":
+            return e.zbc_cv(hw.Rng(SEED, n), P, f, n_steps_S1=500)["mom"]
+        if call == "vega_pathwise":
+            return [e.vega_pathwise(hw.Rng(SEED, n), P, f, n_steps_S1=500)["vega_pathwise_f64"]]
+        if call == "vega_fd":
+            r = e.vega_fd(hw.Rng(SEED, n), P, f, n_steps_S1=500)
+            return [r["price_minus"], r["price_plus"]]
+        if call == "vega_fd_recalibrated":
+            r = e.vega_fd_recalibrated(hw.Rng(SEED, n), n_steps_S1=500)
+            return [r["price_minus_recal"], r["price_plus_recal"]]
+        if call == "vega":
+            r = e.vega(hw.Rng(SEED, n), P, f, n_steps_S1=500)
+            return [r["vega_pathwise_f64"], r["price_minus"], r["price_plus"], r["price_minus_recal"], r["price_plus_recal"]]
+        if call == "fused":
+            r = e.fused(hw.Rng(SEED, n), P, f, n_steps_S1=500)
+            return list(r["P"]) + r["zbc"]["mom"] + [r["vega"]["vega_pathwise_f64"], r["vega"]["price_minus"]]
+        if call == "zbc_cv_batch":
+            res, _ = e.zbc_cv_batch([SEED, SEED + 1, SEED + 2], n, P, f, n_steps_S1=500)
+            return [x for r in res for x in r["mom"]]
+        if call == "vega_pathwise_batch":
+            v, _ = e.vega_pathwise_batch([SEED, SEED + 1], n, P, f, n_steps_S1=500)
+            return list(v)
+        if call == "sample_paths":
+            return list(e.sample_paths(hw.Rng(SEED, n), 4).ravel())
+        return list(e.theta_calibrate(f)["theta_rec"])
+
+    fresh = hw.Engine(device=0)
+    fresh.set_mode(engine.mode)
+    try:
+        first = run(fresh)
+    finally:
+        fresh.close()
+    assert first == run(engine)
+
+
 def test_host_side_caches_follow_the_model(hw, curve):
     """the engine caches host-built tables (model arena, bumped-sigma FD arena) and the (int)(S1/dt) probe; every
     cache must be invalidated by a model change and keyed by its own arguments"""

@@ -216,6 +216,25 @@ def test_vega_sequence_windows(engine, hw, curve):
     assert 0.05 < allres["vega_pathwise"] < 0.5 and 0.05 < allres["vega_fd"] < 0.5    # src/3:789-790
 
 
+def test_vega_sequence_first_call_on_a_fresh_engine(engine, hw, curve):
+    """hw1f_vega as the FIRST pricing call of an engine (no bumped-sigma arena yet, ragged path count) equals the
+    three separate calls on another fresh engine"""
+    n = (1 << 12) + 77
+    a = hw.Engine(device=0)
+    a.set_mode(engine.mode)
+    got = a.vega(hw.Rng(SEED, n), curve["P"], curve["f"], n_steps_S1=500)
+    a.close()
+    b = hw.Engine(device=0)
+    b.set_mode(engine.mode)
+    pw = b.vega_pathwise(hw.Rng(SEED, n), curve["P"], curve["f"], n_steps_S1=500)
+    fd = b.vega_fd(hw.Rng(SEED, n).seek(500), curve["P"], curve["f"], n_steps_S1=500)
+    rc = b.vega_fd_recalibrated(hw.Rng(SEED, n).seek(1000), n_steps_S1=500)
+    b.close()
+    assert got["vega_pathwise"] == pw["vega_pathwise"]
+    assert got["price_minus"] == fd["price_minus"] and got["price_plus"] == fd["price_plus"]
+    assert got["price_minus_recal"] == rc["price_minus_recal"] and got["price_plus_recal"] == rc["price_plus_recal"]
+
+
 def test_batches_equal_single_runs(engine, hw, curve):
     seeds = [1700000000000000 + r * 12345 for r in range(5)]            # src/2:223-229
     res, _ = engine.zbc_cv_batch(seeds, N, curve["P"], curve["f"], n_steps_S1=500)
