@@ -269,6 +269,23 @@ def test_every_entry_point_as_first_call_of_a_fresh_engine(engine, hw, curve, ca
     assert first == run(engine)
 
 
+def test_changing_path_ranges_on_one_engine(engine, hw, curve):
+    """window tables, the per-launch jump table and the scratch buffers are sized per path range: walking through
+    different ranges (sizes, first paths) on ONE engine gives what a fresh engine gives for each of them"""
+    P, f = curve["P"], curve["f"]
+    ranges = [(1 << 14, 0), ((1 << 12) + 77, 0), (1 << 16, 3), (900, (1 << 33) + 5), (1 << 14, 0), (1 << 18, 1 << 20)]
+    for n, first in ranges:
+        z = engine.zbc_cv(hw.Rng(SEED, n, first_path=first), P, f, n_steps_S1=500)["mom"]
+        c = engine.bond_curve(hw.Rng(SEED, n, first_path=first))["P"]
+        fresh = hw.Engine(device=0)
+        fresh.set_mode(engine.mode)
+        try:
+            assert z == fresh.zbc_cv(hw.Rng(SEED, n, first_path=first), P, f, n_steps_S1=500)["mom"], (n, first)
+            assert (c == fresh.bond_curve(hw.Rng(SEED, n, first_path=first))["P"]).all(), (n, first)
+        finally:
+            fresh.close()
+
+
 def test_host_side_caches_follow_the_model(hw, curve):
     """the engine caches host-built tables (model arena, bumped-sigma FD arena) and the (int)(S1/dt) probe; every
     cache must be invalidated by a model change and keyed by its own arguments"""
