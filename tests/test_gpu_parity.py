@@ -238,6 +238,35 @@ def test_vega_sequence_first_call_on_a_fresh_engine(engine, hw, curve):
     assert got["price_minus_recal"] == rc["price_minus_recal"] and got["price_plus_recal"] == rc["price_plus_recal"]
 
 
+@pytest.mark.parametrize("n", [1, 2, 33, 1023, 1025])
+def test_tiny_and_ragged_path_counts(engine, hw, oracle, curve, n):
+    """a single subsequence, less than a warp, one short of / one past a chunk: masks and reductions at the edges"""
+    c = engine.bond_curve(hw.Rng(SEED, n, first_path=7))
+    s, _ = oracle.bond_curve_sums(SEED, n, first_path=7)
+    P, f = oracle.curve_finalize(s, n)
+    assert np.abs(c["P"] / P - 1).max() < 1e-6 and np.abs(c["f"] - f).max() < 5e-6
+    z = engine.zbc_cv(hw.Rng(SEED, n, first_path=7), curve["P"], curve["f"], n_steps_S1=500)
+    mom = oracle.zbc_moments(SEED, n, curve["P"], curve["f"], n_steps_S1=500, first_path=7)
+    # a handful of paths: no averaging of the per-path MUFU-vs-libm differences (the payoff P - K ~ 0.02 amplifies
+    # the 1e-7 of P forty-fold)
+    assert np.allclose(z["mom"], mom, rtol=(2e-5 if n < 64 else 5e-6), atol=1e-12)
+    fu = engine.fused(hw.Rng(SEED, n, first_path=7), curve["P"], curve["f"], n_steps_S1=500)
+    assert (fu["P"] == c["P"]).all() and fu["zbc"]["mom"] == z["mom"]
+
+
+@pytest.mark.parametrize("n_steps", [1000, 998, 2])
+def test_zbc_at_the_ends_of_the_grid(engine, hw, oracle, curve, n_steps):
+    """S1 at the last step of the model, and a two-step option.  The two-step call is far out of the money
+    (P(0.02,10) ~ 0.86 < K = 0.905): only a few paths pay, each by P - K ~ 1e-5, so the X sums are conditioned like
+    1e-7 / 1e-5 -- they are compared at 1e-4, the control-variate sums (no kink) at the usual 5e-6"""
+    S1 = n_steps * 0.01
+    z = engine.zbc_cv(hw.Rng(SEED, N), curve["P"], curve["f"], S1=S1, S2=10.0, n_steps_S1=n_steps)
+    mom = oracle.zbc_moments(SEED, N, curve["P"], curve["f"], S1=S1, S2=10.0, n_steps_S1=n_steps)
+    got = np.asarray(z["mom"])
+    assert np.allclose(got[[1, 3]], mom[[1, 3]], rtol=5e-6)
+    assert np.allclose(got[[0, 2, 4]], mom[[0, 2, 4]], rtol=(1e-4 if n_steps == 2 else 5e-6), atol=1e-12)
+
+
 def test_batches_equal_single_runs(engine, hw, curve):
     seeds = [1700000000000000 + r * 12345 for r in range(5)]            # src/2:223-229
     res, _ = engine.zbc_cv_batch(seeds, N, curve["P"], curve["f"], n_steps_S1=500)
