@@ -286,6 +286,51 @@ def test_changing_path_ranges_on_one_engine(engine, hw, curve):
             fresh.close()
 
 
+def test_two_engines_in_two_threads(engine, hw, curve):
+    """include/hw1f.h: an engine is not thread-safe, engines share nothing but the GPU -- two host threads, one
+    engine each, interleave freely (ctypes releases the GIL inside every call)"""
+    import threading
+    n = (1 << 14) + 5
+    want = {s: engine.zbc_cv(hw.Rng(s, n), curve["P"], curve["f"], n_steps_S1=500)["mom"] for s in range(100, 108)}
+    wantc = {s: engine.bond_curve(hw.Rng(s, n))["P"] for s in range(100, 108)}
+    errors = []
+
+    def worker(seeds):
+        try:
+            e = hw.Engine(device=0)
+            e.set_mode(engine.mode)
+            for _ in range(3):
+                for s in seeds:
+                    if e.zbc_cv(hw.Rng(s, n), curve["P"], curve["f"], n_steps_S1=500)["mom"] != want[s]:
+                        errors.append(("zbc", s))
+                    if not (e.bond_curve(hw.Rng(s, n))["P"] == wantc[s]).all():
+                        errors.append(("curve", s))
+            e.close()
+        except Exception as exc:      # noqa: BLE001
+            errors.append(repr(exc))
+
+    ts = [threading.Thread(target=worker, args=(list(range(100 + 4 * k, 104 + 4 * k)),)) for k in range(2)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errors, errors[:3]
+
+
+def test_batches_longer_than_one_launch(engine, hw, curve):
+    """more seeds than the 32-run seed axis of one launch: the batch entry points loop over launches"""
+    n = 1 << 12
+    seeds = [9000 + 7 * r for r in range(40)]
+    res, _ = engine.zbc_cv_batch(seeds, n, curve["P"], curve["f"], n_steps_S1=500)
+    vega, _ = engine.vega_pathwise_batch(seeds, n, curve["P"], curve["f"], n_steps_S1=500)
+    assert len(res) == 40 and len(vega) == 40
+    for r in (0, 31, 32, 39):
+        one = engine.zbc_cv(hw.Rng(seeds[r], n), curve["P"], curve["f"], n_steps_S1=500)
+        assert res[r]["mom"] == one["mom"] and res[r]["price_cv"] == one["price_cv"]
+        pw = engine.vega_pathwise(hw.Rng(seeds[r], n), curve["P"], curve["f"], n_steps_S1=500)
+        assert vega[r] == pw["vega_pathwise"]
+
+
 def test_host_side_caches_follow_the_model(hw, curve):
     """the engine caches host-built tables (model arena, bumped-sigma FD arena) and the (int)(S1/dt) probe; every
     cache must be invalidated by a model change and keyed by its own arguments"""
