@@ -267,6 +267,21 @@ def test_zbc_at_the_ends_of_the_grid(engine, hw, oracle, curve, n_steps):
     assert np.allclose(got[[0, 2, 4]], mom[[0, 2, 4]], rtol=(1e-4 if n_steps == 2 else 5e-6), atol=1e-12)
 
 
+def test_huge_offsets_and_path_indices(engine, hw, oracle, curve):
+    """normal offsets beyond 32 bits (the Weyl word wraps, T^offset comes from the host jump tables) and path
+    indices just below the 2^41 limit of the window tables"""
+    for first, off in ((0, (1 << 36) + 2), ((1 << 41) - 5000, 0), ((1 << 40) + 3, (1 << 33) + 4)):
+        n = 700
+        st, draws = engine.debug_rng(hw.Rng(SEED, n, first_path=first).seek(off), 699, 6)
+        assert (draws == oracle.draws(SEED, first + 699, 2 * (off // 2), 6)).all(), (first, off)
+        c = engine.bond_curve(hw.Rng(SEED, n, first_path=first).seek(off))
+        s, _ = oracle.bond_curve_sums(SEED, n, first_path=first, offset=off)
+        P, f = oracle.curve_finalize(s, n)
+        assert np.abs(c["P"] / P - 1).max() < 1e-6, (first, off)
+    with pytest.raises(hw.HW1FError):
+        engine.bond_curve(hw.Rng(SEED, 10, first_path=(1 << 42)))
+
+
 def test_batches_equal_single_runs(engine, hw, curve):
     seeds = [1700000000000000 + r * 12345 for r in range(5)]            # src/2:223-229
     res, _ = engine.zbc_cv_batch(seeds, N, curve["P"], curve["f"], n_steps_S1=500)
