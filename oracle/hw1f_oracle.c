@@ -1,5 +1,11 @@
 /*
  * oracle/hw1f_oracle.c -- TEST INFRASTRUCTURE (CPU oracle), not product code.
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load it.
+ *
+ * Parity status: PINNED.  The integer layer (xorwow_ref.c) is bit-exact against cuRAND's own header executed on the
+ * host (tests/golden/xorwow_golden.json, oracle/ref/gen_curand_golden.cu); the float layer is checked against the
+ * outputs of the unmodified reference kernels run on a B200 (tests/golden/ref_b200_seed20251018.json, produced by
+ * oracle/_ref/ref_harness; tests/test_oracle_vs_reference_fixture.py) and against closed-form Hull-White values.
  *
  * Build with -ffp-contract=off: every fused multiply-add below is an explicit
  * fmaf() placed where the reference's sm_100 SASS has an FFMA; everything else
