@@ -39,6 +39,7 @@ extern "C" {
 #define HW1F_ERR_NO_DEVICE 3      /* no usable CUDA device                  */
 #define HW1F_ERR_UNSUPPORTED 4    /* configuration outside the engine       */
 #define HW1F_ERR_NO_MODEL 5       /* hw1f_set_model() not called yet        */
+#define HW1F_ERR_COMM 6           /* moment vector not finite: a peer all-reduce timed out (hw1f_comm_*) */
 
 #define HW1F_ABI_VERSION 1
 
@@ -284,7 +285,9 @@ int hw1f_multi_vega_pathwise(hw1f_multi* m, uint64_t seed, uint64_t n_paths_tota
  *   hw1f_comm_connect: maps the peers' mailboxes; all_handles = world * 64 bytes in rank order;
  *                      cuda_stream = the stream the moments are produced on (engine stream)
  *   hw1f_comm_allreduce: enqueue; every rank must call it the same number of times
- *   hw1f_comm_timeouts: number of bounded-spin expiries so far (0 on a healthy run) */
+ *   hw1f_comm_timeouts: number of bounded-spin expiries so far (0 on a healthy run).  A timed-out call writes
+ *                       NaN into d_data on that rank, and every *_finish call returns HW1F_ERR_COMM for a
+ *                       non-finite moment vector: stale mailbox slots never turn into prices. */
 typedef struct hw1f_comm hw1f_comm;
 int hw1f_comm_create(hw1f_engine* eng, int world, void* ipc_handle64, hw1f_comm** out);
 int hw1f_comm_connect(hw1f_comm* c, int rank, const void* all_handles, void* cuda_stream);

@@ -9,7 +9,7 @@ LIB_PATH = os.environ.get("HW1F_LIB") or os.path.join(HERE, "lib", "libhw1f.so")
 
 OK = 0
 MODE_REFERENCE_ORDER, MODE_DECOMPOSED = 0, 1
-ERR_INVALID, ERR_CUDA, ERR_NO_DEVICE, ERR_UNSUPPORTED, ERR_NO_MODEL = 1, 2, 3, 4, 5
+ERR_INVALID, ERR_CUDA, ERR_NO_DEVICE, ERR_UNSUPPORTED, ERR_NO_MODEL, ERR_COMM = 1, 2, 3, 4, 5, 6
 
 
 class Params(C.Structure):

@@ -677,6 +677,17 @@ int launch_pathwise(hw1f_engine* e, const Launch& L, const ScenDev& sc, int n_st
     return reduce_to(e, L.n_runs, L.grid_x, 2, d_moments);
 }
 
+// a moment vector that went through a timed-out peer all-reduce is NaN-poisoned (hw1f_comm.cu)
+int require_finite(hw1f_engine* e, const double* v, int n)
+{
+    for (int k = 0; k < n; ++k)
+        if (!std::isfinite(v[k])) {
+            e->err = "moment vector is not finite (a peer all-reduce timed out, see hw1f_comm_timeouts)";
+            return HW1F_ERR_COMM;
+        }
+    return HW1F_OK;
+}
+
 // float32 host algebra of src/2:154-179 / :259-290 (+ double extras)
 void zbc_algebra(const double mom[5], uint64_t n_paths_total, float P0S2, int32_t n_steps_S1, hw1f_zbc_result* r)
 {
@@ -800,6 +811,7 @@ const char* hw1f_status_string(int s)
         case HW1F_ERR_NO_DEVICE: return "no CUDA device";
         case HW1F_ERR_UNSUPPORTED: return "unsupported configuration";
         case HW1F_ERR_NO_MODEL: return "model not set";
+        case HW1F_ERR_COMM: return "moment vector not finite (peer all-reduce timed out)";
         default: return "unknown status";
     }
 }
@@ -1125,6 +1137,11 @@ int hw1f_bond_curve_finish(hw1f_engine* e, const double* d_moments, uint64_t n_p
     HW_TRY(check_launch(e, "curve_epilogue_kernel"));
     std::vector<float> host(3 * (size_t)n);
     HW_TRY(download(e, host.data(), dP, host.size() * sizeof(float)));
+    for (int k = 0; k < n; ++k)
+        if (!std::isfinite(host[k])) {
+            e->err = "moment vector is not finite (a peer all-reduce timed out, see hw1f_comm_timeouts)";
+            return HW1F_ERR_COMM;
+        }
     memcpy(P, host.data(), n * sizeof(float));
     memcpy(f, host.data() + n, n * sizeof(float));
     if (P_se) memcpy(P_se, host.data() + 2 * n, n * sizeof(float));
@@ -1195,6 +1212,7 @@ int hw1f_zbc_cv_finish(hw1f_engine* e, const double* d_moments, uint64_t n_paths
     HW_CUDA(e, cudaSetDevice(e->device));
     double mom[5];
     HW_TRY(download(e, mom, d_moments, sizeof(mom)));
+    HW_TRY(require_finite(e, mom, 5));
     zbc_algebra(mom, n_paths_total, P0S2, 0, out);   // the step count is not part of the moments
     return HW1F_OK;
 }
@@ -1287,7 +1305,7 @@ int hw1f_vega_pathwise(hw1f_engine* e, hw1f_rng* rng, float S1, float S2, float 
     HW_TRY(download(e, mom, e->d_moments.p, sizeof(mom)));
     const double np = (double)rng->n_paths;
     out->n_steps_S1 = n;
-    out->vega_pathwise = (float)mom[0] / (float)(int)rng->n_paths;   // sum / N_PATHS in float, src/3:261
+    out->vega_pathwise = (float)mom[0] / (float)rng->n_paths;   // sum / N_PATHS in float, src/3:261
     out->vega_pathwise_f64 = mom[0] / np;
     const double var = (np > 1) ? (mom[1] - mom[0] * mom[0] / np) / (np - 1.0) : 0.0;
     out->vega_pathwise_se = (var > 0) ? sqrt(var / np) : 0.0;
@@ -1319,7 +1337,7 @@ int hw1f_vega_pathwise_batch(hw1f_engine* e, const uint64_t* seeds, int32_t n_ru
         HW_TRY(launch_pathwise(e, L, sc, n, K, e->d_moments.p));
         std::vector<double> mom(2 * (size_t)nb);
         HW_TRY(download(e, mom.data(), e->d_moments.p, mom.size() * sizeof(double)));
-        for (int r = 0; r < nb; ++r) vega[done + r] = (float)mom[2 * r] / (float)(int)n_paths;   // src/3:561
+        for (int r = 0; r < nb; ++r) vega[done + r] = (float)mom[2 * r] / (float)n_paths;   // src/3:561
     }
     HW_CUDA(e, cudaEventRecord(e->ev1, e->stream));
     HW_CUDA(e, cudaEventSynchronize(e->ev1));
@@ -1508,7 +1526,7 @@ int hw1f_vega(hw1f_engine* e, hw1f_rng* rng, float S1, float S2, float K, const 
     const double np = (double)rng->n_paths;
     const float P0S2 = P_mkt[nm - 1];
     out->n_steps_S1 = n;
-    out->vega_pathwise = (float)mom[0] / (float)(int)rng->n_paths;   // sum / N_PATHS in float, src/3:261
+    out->vega_pathwise = (float)mom[0] / (float)rng->n_paths;   // sum / N_PATHS in float, src/3:261
     out->vega_pathwise_f64 = mom[0] / np;
     const double var = (np > 1) ? (mom[1] - mom[0] * mom[0] / np) / (np - 1.0) : 0.0;
     out->vega_pathwise_se = (var > 0) ? sqrt(var / np) : 0.0;
@@ -1633,6 +1651,7 @@ int hw1f_fused_finish(hw1f_engine* e, const double* d_moments, uint64_t n_paths_
     HW_CUDA(e, cudaStreamSynchronize(e->stream));
     std::vector<double> ext(next);
     memcpy(ext.data(), hs, bytes_ext);
+    HW_TRY(require_finite(e, ext.data(), next));
     memcpy(P, hs + bytes_ext, nm * sizeof(float));
     memcpy(f, hs + bytes_ext + nm * sizeof(float), nm * sizeof(float));
     if (P_se) memcpy(P_se, hs + bytes_ext + 2 * nm * sizeof(float), nm * sizeof(float));

@@ -40,38 +40,48 @@ struct CommDev {
     int rank, world;
 };
 
+// system-scope release / acquire on the mailbox flags (the payload stores above the release are plain stores)
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v)
+{
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p)
+{
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
 __global__ void __launch_bounds__(kMaxCount)
 peer_allreduce_kernel(CommDev c, double* __restrict__ data, int count, unsigned epoch)
 {
+    __shared__ int s_timed_out;
     const int i = threadIdx.x;
     const int p = epoch & 1u;
+    if (i == 0) s_timed_out = 0;
     const double mine = (i < count) ? data[i] : 0.0;
     // 1. post into every mailbox (including our own)
     if (i < count)
         for (int r = 0; r < c.world; ++r) c.peer[r]->slots[p][c.rank][i] = mine;
-    __threadfence_system();
+    __threadfence_system();   // every thread's payload stores are ordered before the block-wide barrier ...
     __syncthreads();
-    if (i < c.world) {
-        volatile unsigned* f = &c.peer[i]->flags[p][c.rank];
-        *f = epoch;
-    }
+    if (i < c.world) st_release_sys(&c.peer[i]->flags[p][c.rank], epoch);   // ... and published by the release
     // 2. wait for every peer's post of this epoch in OUR mailbox
     Mailbox* me = c.peer[c.rank];
     if (i < c.world) {
-        volatile unsigned* f = &me->flags[p][i];
         unsigned spins = 0;
-        while (*f != epoch) {
-            if (++spins > kSpinLimit) { atomicAdd(&me->timeouts, 1u); break; }
+        while (ld_acquire_sys(&me->flags[p][i]) != epoch) {
+            if (++spins > kSpinLimit) { atomicAdd(&me->timeouts, 1u); s_timed_out = 1; break; }
             __nanosleep(128);
         }
     }
-    __threadfence_system();
     __syncthreads();
-    // 3. rank-ordered sum
+    // 3. rank-ordered sum; a lost peer poisons the result instead of letting stale slots through: every
+    // *_finish call rejects a non-finite moment vector (HW1F_ERR_COMM)
     if (i < count) {
         double acc = 0.0;
         for (int r = 0; r < c.world; ++r) acc += *(volatile double*)&me->slots[p][r][i];
-        data[i] = acc;
+        data[i] = s_timed_out ? __longlong_as_double(0x7ff8000000000000ll) : acc;
     }
 }
 

@@ -419,7 +419,7 @@ zbc_kernel(StreamGeom g, SeedArgs seeds, ModelDev md, ScenDev sc0, ScenDev sc1, 
     extern __shared__ __align__(16) uint32_t smem[];
     uint32_t* win = smem;
     // drift of steps lead, lead+1, ..: pair k of the main loop reads (d,d,d',d') with one LDS.128
-    const int n_main = n_steps_S1 - lead;                 // steps after the optional lead step
+    const int n_main = max(n_steps_S1 - lead, 0);         // steps after the optional lead step
     const int n_slots = (n_main + 1) >> 1;                // float4 slots per scenario
     float4* drift4 = reinterpret_cast<float4*>(smem + kWinWords);   // [NSCEN][n_slots]
     __shared__ double wpart[kWarps][NSCEN * 5];
@@ -542,7 +542,7 @@ pathwise_kernel(StreamGeom g, SeedArgs seeds, ModelDev md, ScenDev sc, const Bon
     if (tid < kWarps * 2) (&wpart[0][0])[tid] = 0.0;
     const BondPlan pl = plans[0];
     const float2 sg = splat(sc.sig_st), ct = splat(pl.c_t), e2 = splat(md.exp_adt), hdt2 = splat(mul_(0.5f, md.dt));
-    const int n_main = n_steps_S1 - lead;
+    const int n_main = max(n_steps_S1 - lead, 0);
 
     for (unsigned long long chunk = blockIdx.x; chunk < g.n_chunks; chunk += gridDim.x) {
         ThreadStreams t = derive_streams(g, seeds, run, chunk, win);

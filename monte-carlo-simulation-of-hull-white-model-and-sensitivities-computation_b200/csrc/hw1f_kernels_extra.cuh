@@ -27,7 +27,7 @@ __device__ __forceinline__ PairState simulate_to_S1(ThreadStreams& t, const floa
         step1(make_float2(d.x, d.y), ns);
         step1(make_float2(d.z, d.w), nc);
     };
-    const int n_main = n_steps_S1 - lead;
+    const int n_main = max(n_steps_S1 - lead, 0);
     if (lead && n_steps_S1 > 0) {
         float2 ns, nc;
         one_pair(t, ns, nc);
@@ -76,7 +76,7 @@ zbc_sum_kernel(StreamGeom g, SeedArgs seeds, ModelDev md, ScenDev sc, const Bond
 {
     extern __shared__ __align__(16) uint32_t smem[];
     uint32_t* win = smem;
-    const int n_main = n_steps_S1 - lead;
+    const int n_main = max(n_steps_S1 - lead, 0);
     const int n_slots = (n_main + 1) >> 1;
     float4* drift4 = reinterpret_cast<float4*>(smem + kWinWords);
     __shared__ float s_red[kThreads];

@@ -279,7 +279,7 @@ fast_kernel(StreamGeom g, SeedArgs seeds, ModelDev md, FastScen cs0, FastScen cs
                 }
             }
         } else {
-            const int n_main = n_total - lead;
+            const int n_main = max(n_total - lead, 0);   // lead == 1 with zero steps: nothing to do
             if (lead && n_total > 0) {   // cached cos-branch normal of the pair the previous launch opened
                 float2 ns, nc;
                 one_pair(t, ns, nc);

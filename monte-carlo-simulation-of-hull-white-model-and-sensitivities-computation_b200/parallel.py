@@ -36,9 +36,13 @@ def sharded_bond_curve(engine, rng_factory, n_total, device=None):
     world = dist.get_world_size() if dist.is_initialized() else 1
     first, n = shard_paths(n_total, rank, world)
     moments = torch.zeros(2 * engine.n_mat, dtype=torch.float64, device=device or "cuda")
-    torch.cuda.current_stream().synchronize()
+    # the engine launches on ITS stream (its own non-blocking one unless the caller passed stream=...), the
+    # collective runs on torch's current stream: order them explicitly on both sides
+    torch.cuda.current_stream().synchronize()      # the zero-fill above has landed
     engine.bond_curve_moments(rng_factory(first, n), moments.data_ptr())
+    engine.synchronize()                           # the moments are written before NCCL reads them
     allreduce_moments(moments)
+    torch.cuda.current_stream().synchronize()      # ... and reduced before the engine's stream finalises them
     return engine.bond_curve_finish(moments.data_ptr(), n_total)
 
 

@@ -91,3 +91,19 @@ def test_peer_allreduce_kernel_vs_nccl():
                          capture_output=True, text=True, timeout=300)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-3000:]
     assert "peer all-reduce ok on 2 GPUs" in res.stdout
+
+
+def test_sharded_bond_curve_default_engine_stream():
+    """parallel.sharded_bond_curve with an engine on its own stream (stream-ordering race)"""
+    import os
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs at least 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29534",
+                          os.path.join(root, "tools", "sharded_curve_check.py")],
+                         capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-3000:]
+    assert "sharded_bond_curve ok on 2 GPUs" in res.stdout

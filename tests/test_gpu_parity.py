@@ -133,6 +133,22 @@ def test_zbc_moments_vs_oracle(engine, hw, oracle, curve, n_steps, offset):
         assert got["ci95_lo"] < got["price_cv_f64"] < got["ci95_hi"]
 
 
+def test_zbc_zero_steps_any_offset(engine, hw, oracle, curve):
+    """n_steps_S1 == 0 (resolve_steps allows it): the payoff is evaluated at t = 0 whatever the parity of the
+    normal offset -- an odd offset once consumed a Box-Muller pair and took one step"""
+    got = {}
+    for offset in (0, 3):
+        rng = hw.Rng(SEED + 54321, N).seek(offset)
+        got[offset] = engine.zbc_cv(rng, curve["P"], curve["f"], n_steps_S1=0)
+        assert rng.tell() == offset
+        mom = oracle.zbc_moments(SEED + 54321, N, curve["P"], curve["f"], n_steps_S1=0, offset=offset)
+        assert np.allclose(got[offset]["mom"], mom, rtol=2e-4), (got[offset]["mom"], mom)
+    assert got[0]["mom"] == got[3]["mom"]
+    v0 = engine.vega_pathwise(hw.Rng(SEED, N), curve["P"], curve["f"], n_steps_S1=0)
+    v1 = engine.vega_pathwise(hw.Rng(SEED, N).seek(1), curve["P"], curve["f"], n_steps_S1=0)
+    assert v0["vega_pathwise_f64"] == v1["vega_pathwise_f64"]
+
+
 def test_zbc_steps_probe(engine):
     n = engine.steps_to(5.0)
     assert n in (499, 500)
