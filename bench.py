@@ -42,6 +42,16 @@ N_PATHS_LOG2 = 20          # reference N_PATHS = 1024*1024 (include/common.cuh:1
 #      body's SASS is 299 dispatch cycles per 40 path-steps = 7.48)
 #   Q1 save points: reference-order mode adds 4 MUFU.EX2 per 40 path-steps (1.1 MUFU per path-step); decomposed
 #   mode evaluates 2cosh(z)-2 as a polynomial on the FMA pipe (no XU work)
+def workload_string(paths_log2=N_PATHS_LOG2, n_steps=1000, n_mat=101):
+    """the same `config.workload` for both arms: the driver compares the two lines' configs"""
+    return (f"Q1 bond curve P(0,T), f(0,T): 2^{paths_log2} XORWOW subsequences x 2 antithetic paths x {n_steps} steps "
+            f"per GPU, r0=0.012 a=1 sigma=0.1, {n_mat} maturities, seeding included")
+
+
+# committed `ncu --set full` summaries of the dominant kernel per arithmetic mode (tools/ncu_summary.py)
+NCU_CAPTURE = {"decomposed": "profiles/r01_ncu_full_fast_kernel_v3.csv",
+               "reference_order": "profiles/r01_ncu_full_bond_curve_v3.csv"}
+
 ALGO = {
     "decomposed": {"issue": 7.5, "fp32": 2.25, "xu": 1.0},
     "reference_order": {"issue": 12.0, "fp32": 6.75, "xu": 1.1},
@@ -98,6 +108,224 @@ class ClockSampler(threading.Thread):
                 "power_w_max": max(s[3] for s in sel), "samples": len(sel)}
 
 
+def read_ncu_capture(rel_path):
+    """pipe / issue figures of the dominant kernel from the committed `ncu --set full` summary
+    (profiles/*.csv written by tools/ncu_summary.py); nothing is hard-coded here"""
+    import csv
+    path = os.path.join(ROOT, rel_path)
+    if not os.path.exists(path):
+        return {"file": rel_path, "missing": True}
+    m = {}
+    with open(path, newline="") as fh:
+        for row in csv.reader(fh):
+            if len(row) >= 2 and row[0] != "metric":
+                m[row[0]] = row[1]
+
+    def num(key):
+        try:
+            return float(m[key].replace(",", ""))
+        except (KeyError, ValueError):
+            return None
+    issue = num("smsp__issue_active.avg.pct_of_peak_sustained_active")
+    fma_cyc = num("sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active")
+    fma_inst = num("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active")
+    pre, suf = "smsp__average_warps_issue_stalled_", "_per_issue_active.ratio"
+    stalls = {k[len(pre):-len(suf)]: float(v) for k, v in m.items() if k.startswith(pre) and k.endswith(suf)}
+    stalls.pop("selected", None)
+    dram = None
+    if num("dram__bytes_read.sum") is not None:
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        with open(path, newline="") as fh:
+            units = {r[0]: r[2] for r in csv.reader(fh) if len(r) >= 3}
+        dram = sum((num(k) or 0.0) * scale.get(units.get(k, "byte"), 1.0)
+                   for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+    return {
+        "file": rel_path, "source": "committed ncu --set full summary, read at run time (static: not measured in this run)",
+        "kernel_name": m.get("Kernel Name", "")[:60],
+        "kernel_us": num("gpu__time_duration.sum"),
+        "registers": num("launch__registers_per_thread"), "block": num("launch__block_size"),
+        "issue_active_pct": issue,
+        # packed FP32x2 instructions hold the dispatch port for two cycles: port utilisation =
+        # issue-active + (fma-pipe cycles - fma instructions)
+        "dispatch_port_pct": (issue + fma_cyc - fma_inst) if None not in (issue, fma_cyc, fma_inst) else None,
+        "xu_pipe_pct": num("sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active"),
+        "alu_pipe_pct": num("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"),
+        "fma_pipe_cycles_pct": fma_cyc,
+        "top_stall": max(stalls, key=stalls.get) if stalls else None,
+        "dram_bytes": dram,
+    }
+
+
+def _wall_ms(fn, steps, warmup, sync):
+    for i in range(warmup):
+        fn(i)
+    sync()
+    t0 = time.perf_counter()
+    for i in range(steps):
+        fn(100 + i)
+    sync()
+    return (time.perf_counter() - t0) * 1e3 / steps
+
+
+def measure_workloads(eng, hw, n_paths, mkt):
+    """the other north-star workloads (BASELINE.json configs[2], configs[3]) through the public host-buffer API
+    (wall clock, every call returns host results) next to the reference's own host functions on the SAME GPU in the
+    SAME run (oracle/_ref/ref_harness: src/3_sensitivity_analysis.cu:697-834, src/2_option_pricing.cu:210-468,
+    src/3:527-654).  Outside every timed region of the headline metric."""
+    import tempfile
+    P, f = mkt["P"], mkt["f"]
+    sync = eng.synchronize
+    out = {}
+
+    def add(key, ms, what):
+        out[key] = {"engine_ms": ms, "reference_ms": None, "ratio": None, "what": what}
+
+    add("q1_bond_curve", _wall_ms(lambda i: eng.bond_curve(hw.Rng(i, n_paths)), 20, 3, sync),
+        "hw1f_bond_curve vs init_rng + simulate_zcb + compute_average_and_forward + D2H")
+    add("q2b_zbc_cv", _wall_ms(lambda i: eng.zbc_cv(hw.Rng(i, n_paths), P, f), 20, 3, sync),
+        "hw1f_zbc_cv vs init_rng + simulate_ZBC_control_variate + D2H of 5 moments (src/2:107-208)")
+    add("q3_pathwise", _wall_ms(lambda i: eng.vega_pathwise(hw.Rng(i, n_paths), P, f), 20, 3, sync),
+        "hw1f_vega_pathwise vs init_rng + simulate_sensitivity + D2H (src/3:236-272)")
+    add("q3_sequence", _wall_ms(lambda i: eng.vega(hw.Rng(i, n_paths), P, f), 10, 2, sync),
+        "hw1f_vega (reference draw windows: pathwise [0,500), CRN FD [500,1000), recalibrated FD [1000,2000)) vs "
+        "init_rng + run_sensitivity_mc + run_finite_difference + run_finite_difference_recalibrated (src/3:697-834)")
+    add("q3_single_window", _wall_ms(lambda i: eng.fused(hw.Rng(i, n_paths), P, f), 10, 2, sync),
+        "hw1f_fused: curve + ZBC/CV + pathwise vega + CRN FD bumps on ONE window of normals (statistically equivalent "
+        "to the Q3 sequence, not stream-identical; no reference counterpart)")
+    add("zbc_validation_20_seeds",
+        _wall_ms(lambda i: eng.zbc_cv_batch([i * 1000003 + r * 12345 for r in range(20)], n_paths, P, f), 5, 1, sync),
+        "hw1f_zbc_cv_batch (20 seeds, one launch) vs run_zbc_statistical_validation (src/2:210-468)")
+    add("vega_validation_20_seeds",
+        _wall_ms(lambda i: eng.vega_pathwise_batch([i * 1000003 + r * 982451653 for r in range(20)], n_paths, P, f),
+                 5, 1, sync),
+        "hw1f_vega_pathwise_batch (20 seeds, one launch) vs run_statistical_validation (src/3:527-654)")
+
+    harness = os.path.join(ROOT, "oracle", "_ref", "ref_harness")
+    if not os.path.exists(harness):
+        out["reference"] = "oracle/_ref/ref_harness not built: engine times only"
+        return out
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", "0").split(",")[0])
+    with tempfile.TemporaryDirectory() as td:
+        os.makedirs(os.path.join(td, "data"))
+
+        def run(args, key_json):
+            o = os.path.join(td, "o.json")
+            try:
+                subprocess.run([harness] + args + [o], check=True, cwd=td, env=env, stdout=subprocess.DEVNULL,
+                               stderr=subprocess.DEVNULL, timeout=600)
+                with open(o) as fh:
+                    return json.load(fh)[key_json]
+            except Exception as exc:   # noqa: BLE001  (a failed reference leg leaves the engine numbers standing)
+                print(f"[bench] reference leg {args} failed: {exc}", file=sys.stderr)
+                return None
+        ref = {
+            "q1_bond_curve": run(["bench", "q1", "20", "3"], "workload_ms_per_step"),
+            "q2b_zbc_cv": run(["bench", "q2", "20", "3"], "workload_ms_per_step"),
+            "q3_pathwise": run(["bench", "q3", "20", "3"], "workload_ms_per_step"),
+            "q3_sequence": run(["workload", "q3seq", "10", "2"], "wall_ms_per_step"),
+            "zbc_validation_20_seeds": run(["workload", "zbc20", "3", "1"], "wall_ms_per_step"),
+            "vega_validation_20_seeds": run(["workload", "vega20", "3", "1"], "wall_ms_per_step"),
+        }
+    for k, v in ref.items():
+        if v is not None:
+            out[k]["reference_ms"] = v
+            out[k]["ratio"] = v / out[k]["engine_ms"]
+    out["note"] = ("engine: wall ms per public call, host buffers in and out; reference: q1/q2b/q3_pathwise CUDA-event "
+                   "time of init_rng + kernel + D2H, the others wall ms of its own host functions (cudaMalloc/cudaFree "
+                   "and 50 MB state copies included -- that part varies several-fold between boxes)")
+    return out
+
+
+CLOSED_FORM = {"P_0_5": 0.947126, "P_0_10": 0.859387, "zbc": 0.025255}   # continuous-time HW values, SURVEY 0.1
+
+
+def scaling_run(eng, hw, torch, dist, dev, stream, rank, world, peer, mkt, total_log2):
+    """BASELINE.json configs[4]: 2^30 XORWOW subsequences (2^31 antithetic paths) x 1000 steps, curve + ZBC/control variate
+    + antithetic pathwise vega + both CRN FD bumps from ONE fused launch per rank, sharded by contiguous subsequence
+    range (strong scaling), ONE all-reduce of 220 doubles, hw1f_fused_finish on every rank.  Device-timed, max over ranks."""
+    nm, n_steps = eng.n_mat, eng.n_steps
+    total = 1 << total_log2
+    first, count = hw.package.parallel.shard_paths(total, rank, world)
+    mom = torch.zeros(2 * nm + 18, dtype=torch.float64, device=dev)
+
+    def one_pass(seed):
+        eng.fused_moments(hw.Rng(seed, count, first_path=first), mkt["P"], mkt["f"], mom.data_ptr(), eps=0.001,
+                          n_steps_S1=500)
+        if peer is not None:
+            peer.all_reduce(mom)
+        elif world > 1:
+            dist.all_reduce(mom)
+
+    one_pass(20251019)          # builds the seed-independent jump tables of this shard (untimed)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    one_pass(20251018)
+    e1.record()
+    torch.cuda.synchronize()
+    secs = torch.tensor([e0.elapsed_time(e1) * 1e-3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(secs, op=dist.ReduceOp.MAX)
+    res = eng.fused_finish(mom.data_ptr(), total, float(mkt["P"][-1]), eps=0.001, n_steps_S1=500)
+    z, v = res["zbc"], res["vega"]
+    s = float(secs.item())
+    return {
+        "workload": f"configs[4]: fused curve + ZBC/CV + antithetic pathwise vega + CRN FD bumps, 2^{total_log2} "
+                    f"subsequences x 2 antithetic x {n_steps} steps, ONE launch per rank + one all-reduce of "
+                    f"{2 * nm + 18} doubles", "scaling": "strong", "n_gpus": world, "subsequences_per_gpu": count,
+        "seconds": s, "path_steps_per_s": 2.0 * total * n_steps / s,
+        "P_0_5": float(res["P"][50]), "P_0_10": float(res["P"][100]), "P_0_10_se": float(res["P_se"][100]),
+        "zbc_price_cv": z["price_cv_f64"], "zbc_se_cv": z["se_cv"], "beta": z["beta_f64"],
+        "vega_pathwise": v["vega_pathwise_f64"], "vega_pathwise_se": v["vega_pathwise_se"], "vega_fd": v["vega_fd"],
+        "closed_form": CLOSED_FORM,
+        "note": "estimators must be identical on every GPU count: the shards' union is the single-GPU path set; the "
+                "distance from the continuous-time values is the reference scheme's O(dt^2) / grid-interpolation bias "
+                "plus the 2^20-path noise of the market curve the option is priced on",
+    }
+
+
+def multi_gpu_check(eng, hw, torch, dist, dev, rank, world, peer, mkt):
+    """N > 1: every rank simulates its shard of ONE 2^18-subsequence set, the moment vectors are all-reduced (own NVLink
+    peer kernel and NCCL), and every rank also simulates the whole set alone: sums must agree to double rounding.
+    Once for the Q1 vector (202 doubles), once for the fused vector (220 doubles)."""
+    hwp = hw.package.parallel
+    total, seed = 1 << 18, 77001
+    first, count = hwp.shard_paths(total, rank, world)
+    nm = eng.n_mat
+    out = {"set": "2^18 subsequences, seed 77001", "tolerance_fail": 1e-6}
+
+    def rel(a, b):
+        return float(((a - b).abs() / b.abs().clamp_min(1e-300)).max())
+
+    for name, n, sim in (
+        ("curve", 2 * nm, lambda r, m: eng.bond_curve_moments(r, m.data_ptr())),
+        ("fused", 2 * nm + 18, lambda r, m: eng.fused_moments(r, mkt["P"], mkt["f"], m.data_ptr(), eps=0.001,
+                                                                 n_steps_S1=500)),
+    ):
+        single = torch.zeros(n, dtype=torch.float64, device=dev)
+        sim(hw.Rng(seed, total), single)
+        shard = torch.zeros(n, dtype=torch.float64, device=dev)
+        sim(hw.Rng(seed, count, first_path=first), shard)
+        torch.cuda.synchronize()
+        via_nccl = shard.clone()
+        dist.all_reduce(via_nccl)
+        out[name + "_nccl_vs_single_max_rel"] = rel(via_nccl, single)
+        if peer is not None:
+            via_peer = shard.clone()
+            peer.all_reduce(via_peer)
+            torch.cuda.synchronize()
+            out[name + "_peer_vs_single_max_rel"] = rel(via_peer, single)
+            out[name + "_peer_vs_nccl_max_rel"] = rel(via_peer, via_nccl)
+    worst = max(v for k, v in out.items() if k.endswith("_vs_single_max_rel"))
+    w = torch.tensor([worst], dtype=torch.float64, device=dev)
+    dist.all_reduce(w, op=dist.ReduceOp.MAX)
+    out["multi_vs_single_max_rel"] = float(w.item())
+    out["ok"] = bool(out["multi_vs_single_max_rel"] <= out["tolerance_fail"])
+    return out
+
+
 def run_reference_arm(args, rank, real_stdout):
     """the reference's own CUDA implementation of the path (the reference has no CPU path), driven
     by oracle/_ref/ref_harness on GPU 0; falls back to the OpenMP oracle port if it was not built"""
@@ -108,8 +336,10 @@ def run_reference_arm(args, rank, real_stdout):
     line = {"metric": METRIC, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "Q1 bond curve: 2^20 subsequences x 2 antithetic x 1000 steps (reference "
-                                   "simulate_zcb), seeds pinned",
+            "config": {"workload": workload_string(),
+                       "paths_per_gpu": 2 * n_paths, "n_steps": 1000,
+                       "arithmetic": "reference kernels (init_rng + simulate_zcb + compute_average_and_forward), seeds pinned",
+                       "l2": "not flushed (the reference re-reads its own 50 MB state array every step)",
                        "parallelism": "single GPU on rank 0 (the reference has no multi-GPU path)"}}
     if os.path.exists(harness):
         out = os.path.join(ROOT, "gpurun_out", "ref_bench_q1.json")
@@ -165,6 +395,10 @@ def main():
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--paths-log2", type=int, default=N_PATHS_LOG2, help="subsequences per GPU (default 2^20)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-workloads", action="store_true", help="skip the Q2b / Q3 / 20-seed workload block (N = 1)")
+    ap.add_argument("--no-scaling-run", action="store_true", help="skip the configs[4] fused 2^30 strong-scaling pass")
+    ap.add_argument("--scaling-log2", type=int, default=30, help="total subsequences of the scaling run (default 2^30)")
+    ap.add_argument("--ncu-capture", default=None, help="committed ncu summary CSV the roofline object cites")
     ap.add_argument("--collective", default="peer", choices=["peer", "nccl"],
                     help="moment all-reduce for N > 1: own NVLink peer-memory kernel (hw1f_comm_*) or NCCL")
     ap.add_argument("--mode", default="decomposed", choices=["decomposed", "reference_order"],
@@ -324,9 +558,51 @@ def main():
     other_ms = e0.elapsed_time(e1) / n_other
     eng.set_mode(hw._ffi.MODE_DECOMPOSED if args.mode == "decomposed" else hw._ffi.MODE_REFERENCE_ORDER)
 
+    # ---- one longer sustained figure: ~1 s of back-to-back steps under one event pair (no flush: the step's only
+    # inputs are the 17 KB model tables and the L2-resident jump tables) ----
+    n_sus = max(200, int(round(1000.0 / max(ms_per_step, 1e-3))))
+    for i in range(3):
+        device_step(1000 + i)
+    barrier()
+    e0.record()
+    for i in range(n_sus):
+        device_step(30000 + i)
+    e1.record()
+    torch.cuda.synchronize()
+    sus = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(sus, op=dist.ReduceOp.MAX)
+    sus_ms = float(sus.item())
+    sustained = {"steps": n_sus, "seconds": sus_ms * 1e-3, "ms_per_step": sus_ms / n_sus,
+                 "value": path_steps_per_step * n_sus / (sus_ms * 1e-3),
+                 "note": "back-to-back steps, one event pair, max over ranks, L2 not flushed"}
+
+    # ---- market curve for the option workloads: a prior Q1 at 2^20 subsequences, fixed seed (identical on every rank) ----
+    mkt = eng.bond_curve(hw.Rng(1234, 1 << 20))
+
+    # ---- N > 1: sharded moments against the single-GPU moments of the same path set (fails the run above 1e-6) ----
+    multi_check = None
+    if world > 1:
+        multi_check = multi_gpu_check(eng, hw, torch, dist, dev, rank, world, peer, mkt)
+
+    # ---- the other north-star workloads next to the reference's own host functions (N = 1, rank 0) ----
+    workloads = None
+    if world == 1 and not args.no_workloads:
+        workloads = measure_workloads(eng, hw, n_paths, mkt)
+
+    # ---- BASELINE.json configs[4]: the 2^30 fused strong-scaling run on every N ----
+    scal = None
+    if not args.no_scaling_run:
+        scal = scaling_run(eng, hw, torch, dist, dev, stream, rank, world, peer, mkt, args.scaling_log2)
+    peer_timeouts = peer.timeouts() if peer is not None else 0
+    if collective_check is not None:
+        collective_check["timeouts"] = peer_timeouts
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
+        if multi_check is not None and not multi_check["ok"]:
+            sys.exit(3)
         return
 
     # ---- roofline denominators measured here: issue rate and pipe rates of this GPU ----
@@ -353,7 +629,9 @@ def main():
         "frac": max(xu_frac, issue_frac),
         # dram__bytes_read.sum + dram__bytes_write.sum of one simulation-kernel launch
         # (profiles/r01_ncu_full_*.csv): window tables, L2-resident after first touch
-        "traffic": 6635008, "traffic_unit": "bytes per launch (ncu --set full)",
+        "traffic": read_ncu_capture(args.ncu_capture or NCU_CAPTURE[args.mode]).get("dram_bytes"),
+        "traffic_unit": "bytes per launch: dram__bytes_read.sum + dram__bytes_write.sum of the committed ncu --set full "
+                        "capture (window tables re-read after the L2 flush; algorithmic bytes are 17 KB in, 1.6 KB out)",
         "peak_source": "measured by hw1f_pipe_probe on this GPU in this run (MUFU.EX2 / FFMA / LOP3 / mixed streams); "
                        "MEASURED_PEAKS.json has no FP32/XU entry (HBM and bf16 tensor only)",
         "mode": args.mode,
@@ -365,13 +643,9 @@ def main():
         "probes_Ginstr_s": {"ffma": ffma / 1e9, "ffma2": ffma2 / 1e9, "mufu_ex2": mufu / 1e9, "lop3_shf": alu / 1e9,
                             "i2fp": i2f / 1e9, "hw1f_mix": mix / 1e9},
         "algorithmic_per_path_step": algo,
-        # static, from the committed ncu --set full capture of this kernel (not measured in this run): the dispatch
-        # port is the binding resource -- packed FP32x2 instructions hold it for two cycles, so its utilisation is
-        # issue-active + (fma-pipe cycles - fma instructions)
-        "ncu_capture": ({"file": "profiles/r01_ncu_full_fast_kernel_v3.csv", "kernel_us": 572.7, "issue_active_pct": 81.2,
-                         "dispatch_port_pct": 94.0, "xu_pipe_pct": 80.7, "alu_pipe_pct": 65.6, "fma_pipe_cycles_pct": 43.5,
-                         "top_stall": "not_selected"} if args.mode == "decomposed" else
-                        {"file": "profiles/r01_ncu_full_bond_curve_v3.csv"}),
+        # from the committed ncu --set full summary of this kernel (read from the CSV at run time, not measured in
+        # this run): the dispatch port is the co-binding resource -- packed FP32x2 instructions hold it for two cycles
+        "ncu_capture": read_ncu_capture(args.ncu_capture or NCU_CAPTURE[args.mode]),
         "kernel": ("fast_kernel<1,0,0>" if args.mode == "decomposed" else "bond_curve_kernel<1>") +
                   " (prep_lo_kernel + reduce_curve_kernel included in the time)",
         "other_mode": {"mode": other, "ms_per_step": other_ms,
@@ -404,9 +678,7 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"Q1 bond curve P(0,T), f(0,T): 2^{args.paths_log2} XORWOW subsequences x 2 antithetic "
-                               f"paths x {n_steps} steps per GPU, r0=0.012 a=1 sigma=0.1, {n_mat} maturities, "
-                               "seeding included", "arithmetic": args.mode,
+        "config": {"workload": workload_string(args.paths_log2, n_steps, n_mat), "arithmetic": args.mode,
                    "paths_per_gpu": 2 * n_paths, "n_steps": n_steps, "l2": "flushed between steps (256 MiB memset, "
                    "outside the per-step event pairs)", "parallelism": (f"path-range sharding x{world}, one all-reduce of 202 doubles per step "
                                                            f"({collective})") if world > 1 else "single GPU"},
@@ -419,12 +691,23 @@ def main():
         "clocks": clocks, "clock_check": "rejected: thermal/hw slowdown seen" if bad else "ok",
         "roofline": roofline,
         "cpu_baseline": cpu_baseline,
-        "check": {"P_0_10": float(last["P"][-1]), "f_0_0": float(last["f"][0])},
+        "sustained": sustained,
+        "workloads": workloads,
+        "scaling_run": scal,
+        "check": {"P_0_10": float(last["P"][-1]), "f_0_0": float(last["f"][0]),
+                  "multi_vs_single_max_rel": multi_check["multi_vs_single_max_rel"] if multi_check else None,
+                  "multi_gpu": multi_check},
         "published_v100_path_steps_per_s": 3.91e11,
     }
     _emit(line, real_stdout)
     if world > 1:
         dist.destroy_process_group()
+    if multi_check is not None and not multi_check["ok"]:
+        print(f"[bench] multi-GPU moments differ from the single-GPU moments: {multi_check}", file=sys.stderr)
+        sys.exit(3)
+    if peer_timeouts:
+        print(f"[bench] peer all-reduce timed out {peer_timeouts} times", file=sys.stderr)
+        sys.exit(4)
 
 
 if __name__ == "__main__":

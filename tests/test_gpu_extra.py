@@ -50,18 +50,27 @@ def test_fused_equals_separate_passes(engine, hw, curve):
     assert abs(both - sep_v[0] / N) < 0.02                              # antithetic twin: same estimand
 
 
-def test_reduction_bench_methods(engine, hw, curve):
-    rng = hw.Rng(SEED, 1 << 18)
-    ref = engine.zbc_cv(hw.Rng(SEED, 1 << 18), curve["P"], curve["f"], n_steps_S1=500)
-    prices = []
+def test_reduction_bench_methods(engine, hw, curve, oracle):
+    """hw1f_reduction_bench (perf_benchmark.cuh:19-197, src/benchmark_reductions.cu:17-72) against the ORACLE: every
+    launch continues the streams, so launch j of the shared handle sees normals [500 j, 500 j + 500)"""
+    n, steps = 1 << 16, 500
+    P, f = curve["P"], curve["f"]
+    rng = hw.Rng(SEED, n)
+    launches_per_method = 3                                   # 1 warm-up + 2 timed; the price is the LAST launch's
     for method in range(4):
-        r = engine.reduction_bench(rng, method, curve["P"], curve["f"], n_steps_S1=500, n_warmup=1, n_runs=2)
+        r = engine.reduction_bench(rng, method, P, f, n_steps_S1=steps, n_warmup=1, n_runs=2)
         assert r["avg_ms"] > 0
-        prices.append(r["price"])
-        assert abs(r["price"] - ref["price_raw"]) < 8 * ref["se_raw"] + 1e-6
-    assert rng.tell() == 4 * 3 * 500
-    # deterministic tree on the same window as zbc_cv reproduces its raw price
-    one = engine.reduction_bench(hw.Rng(SEED, 1 << 18), 3, curve["P"], curve["f"], n_steps_S1=500, n_warmup=0, n_runs=1)
+        last = method * launches_per_method + launches_per_method - 1
+        mom = oracle.zbc_moments(SEED, n, P, f, n_steps_S1=steps, offset=last * steps)
+        want = mom[0] / (2.0 * n)
+        if method == 3:      # deterministic two-level tree in double: the oracle's sum to float32 rounding
+            assert r["price"] == pytest.approx(want, rel=3e-6), (method, r["price"], want)
+        else:                # float32 atomics (order-dependent rounding, like the reference's): measured <= 2e-5
+            assert r["price"] == pytest.approx(want, rel=1e-4), (method, r["price"], want)
+    assert rng.tell() == 4 * launches_per_method * steps
+    # the tree on the window of zbc_cv reproduces its raw price
+    ref = engine.zbc_cv(hw.Rng(SEED, n), P, f, n_steps_S1=steps)
+    one = engine.reduction_bench(hw.Rng(SEED, n), 3, P, f, n_steps_S1=steps, n_warmup=0, n_runs=1)
     assert one["price"] == pytest.approx(ref["price_raw"], rel=1e-6)
 
 
@@ -153,6 +162,22 @@ def test_drivers_match_reference_binaries(driver_runs):
     zr = np.loadtxt(ref / "data" / "zbc_bootstrap_optimal.csv", delimiter=",", skiprows=1)
     assert np.abs(zm[:, 1] / zr[:, 1] - 1).max() < 1e-4      # CV-adjusted prices
     assert np.abs(zm[:, 2] / zr[:, 2] - 1).max() < 1e-4      # raw prices
+    # theta recovered from each driver's own forward curve (recover_theta, src/2:14-35): d theta ~ 10 x d f
+    tm = np.loadtxt(mine / "data" / "theta_comparison.csv", delimiter=",", skiprows=1)
+    tr = np.loadtxt(ref / "data" / "theta_comparison.csv", delimiter=",", skiprows=1)
+    assert (tm[:, 0] == tr[:, 0]).all() and np.abs(tm[:, 1] - tr[:, 1]).max() == 0     # T grid, analytic theta
+    assert np.abs(tm[10:, 2] - tr[10:, 2]).max() < 10 * np.abs(fm[9:] - fr[9:]).max() + 1e-6
+    # the reduction benchmark (src/benchmark_reductions.cu:74-212): same seed, every launch continues the streams, so
+    # method k of both drivers prices the same window with the same strategy; float32 atomics on both sides
+    assert logs["ref_benchmark"].returncode == 0, logs["ref_benchmark"].stdout[-1500:]
+    bm = json.load(open(mine / "data" / "benchmark_reductions.json"))["results"]
+    br = json.load(open(ref / "data" / "benchmark_reductions.json"))["results"]
+    assert len(br) == 3 and [r["method"] for r in br] == [r["method"] for r in bm[:3]]
+    for a, b in zip(bm[:3], br):
+        assert a["price"] == pytest.approx(b["price"], rel=1e-4), (a, b)
+    # the fourth method (deterministic tree, no reference counterpart) prices the next window: same estimand
+    se = 0.045 / np.sqrt(2.0 * (1 << 20))                      # sd of the discounted payoff ~ 0.045
+    assert abs(bm[3]["price"] - np.mean([r["price"] for r in br])) < 6 * se
 
 
 def test_fused_with_fd_bumps_one_launch(engine, hw, curve):
