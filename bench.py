@@ -251,9 +251,7 @@ def scaling_run(eng, hw, torch, dist, dev, stream, rank, world, peer, mkt, total
     def one_pass(seed):
         eng.fused_moments(hw.Rng(seed, count, first_path=first), mkt["P"], mkt["f"], mom.data_ptr(), eps=0.001,
                           n_steps_S1=500)
-        if peer is not None:
-            peer.all_reduce(mom)
-        elif world > 1:
+        if peer is None and world > 1:     # with the peers attached the kernel's last block has already exchanged
             dist.all_reduce(mom)
 
     one_pass(20251019)          # builds the seed-independent jump tables of this shard (untimed)
@@ -299,6 +297,8 @@ def multi_gpu_check(eng, hw, torch, dist, dev, rank, world, peer, mkt):
     def rel(a, b):
         return float(((a - b).abs() / b.abs().clamp_min(1e-300)).max())
 
+    if peer is not None:
+        peer.attach(False)
     for name, n, sim in (
         ("curve", 2 * nm, lambda r, m: eng.bond_curve_moments(r, m.data_ptr())),
         ("fused", 2 * nm + 18, lambda r, m: eng.fused_moments(r, mkt["P"], mkt["f"], m.data_ptr(), eps=0.001,
@@ -314,10 +314,18 @@ def multi_gpu_check(eng, hw, torch, dist, dev, rank, world, peer, mkt):
         out[name + "_nccl_vs_single_max_rel"] = rel(via_nccl, single)
         if peer is not None:
             via_peer = shard.clone()
-            peer.all_reduce(via_peer)
+            peer.all_reduce(via_peer)                  # the exchange as a launch of its own
+            peer.attach(True)
+            via_tail = torch.zeros(n, dtype=torch.float64, device=dev)
+            sim(hw.Rng(seed, count, first_path=first), via_tail)   # exchanged by the kernel's last block
+            peer.attach(False)
             torch.cuda.synchronize()
             out[name + "_peer_vs_single_max_rel"] = rel(via_peer, single)
-            out[name + "_peer_vs_nccl_max_rel"] = rel(via_peer, via_nccl)
+            out[name + "_tail_vs_single_max_rel"] = rel(via_tail, single)
+            out[name + "_tail_vs_nccl_max_rel"] = rel(via_tail, via_nccl)
+            out[name + "_tail_bit_identical_to_peer_kernel"] = bool((via_tail == via_peer).all())
+    if peer is not None:
+        peer.attach(True)
     worst = max(v for k, v in out.items() if k.endswith("_vs_single_max_rel"))
     w = torch.tensor([worst], dtype=torch.float64, device=dev)
     dist.all_reduce(w, op=dist.ReduceOp.MAX)
@@ -462,15 +470,18 @@ def main():
                 want_peer[0] = 0
         dist.all_reduce(want_peer, op=dist.ReduceOp.MIN)   # all ranks or none
         if int(want_peer.item()) == 1:
-            collective = "peer_nvlink_kernel"
+            # attached: the LAST BLOCK of every *_moments simulation kernel posts the reduced vector to the peers'
+            # mailboxes and sums the slots in rank order itself -- no launch between reduction and exchange
+            collective = "peer_nvlink_in_kernel_tail"
+            peer.attach(True)
         elif peer is not None:
             peer.close()
             peer = None
 
     def reduce_moments():
         if peer is not None:
-            peer.all_reduce(moments)
-        elif world > 1:
+            return                 # done inside the simulation kernel's tail
+        if world > 1:
             dist.all_reduce(moments)
 
     def device_step(seed):
@@ -481,6 +492,8 @@ def main():
     def e2e_step(seed):
         eng.set_model(eng.params)                    # compute_constants(): H2D of the model tables
         rng = hw.Rng(seed, n_paths, first_path=first_path)
+        if world == 1:
+            return eng.bond_curve(rng, timing=False)   # the one-call public API: P, f, P_se land in host buffers
         eng.bond_curve_moments(rng, moments.data_ptr())
         reduce_moments()
         return eng.bond_curve_finish(moments.data_ptr(), n_paths * world)   # D2H of P, f, P_se
@@ -506,7 +519,7 @@ def main():
         flush.zero_()
     barrier()
     t_load1 = time.time()
-    launches = eng.launch_count - launches0 + (args.steps if peer is not None else 0)
+    launches = eng.launch_count - launches0
     step_ms = [a.elapsed_time(b) for a, b in ev]
     total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
     if world > 1:
@@ -532,11 +545,13 @@ def main():
     clocks = sampler.summary(t_load0, t_load2)
 
     collective_check = None
-    if peer is not None:   # same local moments through both collectives (every rank takes part)
+    if peer is not None:   # the same shard moments: exchanged in the kernel tail vs NCCL (every rank takes part)
+        peer.attach(False)
         eng.bond_curve_moments(hw.Rng(424242, n_paths, first_path=first_path), moments.data_ptr())
         via_nccl = moments.clone()
-        peer.all_reduce(moments)
         dist.all_reduce(via_nccl)
+        peer.attach(True)
+        eng.bond_curve_moments(hw.Rng(424242, n_paths, first_path=first_path), moments.data_ptr())
         torch.cuda.synchronize()
         rel = float(((moments - via_nccl).abs() / (via_nccl.abs() + 1e-300)).max())
         collective_check = {"max_rel_diff_vs_nccl": rel, "timeouts": peer.timeouts()}

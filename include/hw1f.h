@@ -279,7 +279,7 @@ int hw1f_multi_vega_pathwise(hw1f_multi* m, uint64_t seed, uint64_t n_paths_tota
 /* The path's single exchange step -- summing the packed double moment vector over ranks -- as ONE own
  * kernel over NVLink peer memory instead of an NCCL call: every rank posts its vector into a mailbox
  * of every peer (CUDA IPC mapping), raises a system-scope flag, waits (bounded) for the peers' flags
- * and sums the slots in rank order, so the result is bit-identical on all ranks.  count <= 256, world <= 8.
+ * and sums the slots in rank order, so the result is bit-identical on all ranks.  count <= 512, world <= 8.
  *   hw1f_comm_create : allocates this rank's mailbox, returns its 64-byte cudaIpcMemHandle_t
  *   (exchange the handles with any out-of-band all-gather, e.g. torch.distributed)
  *   hw1f_comm_connect: maps the peers' mailboxes; all_handles = world * 64 bytes in rank order;
@@ -292,6 +292,11 @@ typedef struct hw1f_comm hw1f_comm;
 int hw1f_comm_create(hw1f_engine* eng, int world, void* ipc_handle64, hw1f_comm** out);
 int hw1f_comm_connect(hw1f_comm* c, int rank, const void* all_handles, void* cuda_stream);
 int hw1f_comm_allreduce(hw1f_comm* c, double* d_data, int32_t count);
+/* on != 0: from now on every hw1f_*_moments entry point of the communicator's engine (bond curve, ZBC, pathwise, fused)
+ * returns the ALL-REDUCED vector: the last block of the simulation kernel's reduction posts it to the peers and sums
+ * the slots in rank order itself -- no launch between reduction and exchange.  Every rank must make the same calls in
+ * the same order.  The one-call entry points (hw1f_bond_curve, hw1f_zbc_cv, ...) stay local.  on = 0 detaches. */
+int hw1f_comm_attach(hw1f_comm* c, int on);
 int hw1f_comm_timeouts(hw1f_comm* c, uint32_t* n);
 int hw1f_comm_destroy(hw1f_comm* c);
 const char* hw1f_comm_last_error(const hw1f_comm* c);

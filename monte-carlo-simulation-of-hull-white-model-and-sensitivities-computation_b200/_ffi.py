@@ -124,6 +124,7 @@ SYMBOLS = {
     "hw1f_comm_create": (C.c_int, [_P, C.c_int, _P, C.POINTER(_P)]),
     "hw1f_comm_connect": (C.c_int, [_P, C.c_int, _P, _P]),
     "hw1f_comm_allreduce": (C.c_int, [_P, _P, C.c_int32]),
+    "hw1f_comm_attach": (C.c_int, [_P, C.c_int]),
     "hw1f_comm_timeouts": (C.c_int, [_P, C.POINTER(C.c_uint32)]),
     "hw1f_comm_destroy": (C.c_int, [_P]),
     "hw1f_comm_last_error": (C.c_char_p, [_P]),

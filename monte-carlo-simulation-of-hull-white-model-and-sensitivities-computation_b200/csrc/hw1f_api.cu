@@ -11,11 +11,13 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "hw1f_kernels.cuh"
 #include "hw1f_kernels_extra.cuh"
 #include "hw1f_kernels_fast.cuh"
+#include "hw1f_tail.cuh"
 #include "hw1f_probe.cuh"
 #include "xorwow_jump.hpp"
 
@@ -27,6 +29,9 @@ struct hw1f_rng {
 };
 
 namespace {
+
+constexpr int kTailCounters = 64;      // ticket counters of the tail kernel: one per run
+constexpr int kResAreas = 4;           // result areas in mapped pinned host memory
 
 template <class T>
 struct DevBuf {
@@ -108,6 +113,16 @@ struct hw1f_engine {
     bool fd_cached = false;
     float fd_sig[2] = {0.f, 0.f};
     cudaEvent_t ev_fd = nullptr;
+    // tail of the simulation kernels (hw1f_tail.cuh): ticket counters, group partials, and the result areas in mapped
+    // pinned host memory the last block stores into (the host only waits for the stream)
+    DevBuf<unsigned> d_tail_cnt;
+    DevBuf<double> d_gpart;
+    char* h_res = nullptr;
+    size_t res_area_bytes = 0, res_doubles = 0;
+    // peers attached with hw1f_comm_attach: the *_moments entry points all-reduce in their tail
+    bool comm_on = false;
+    CommDev comm{};
+    unsigned* comm_epoch = nullptr;
     // (int)(S1/d_dt) as the device evaluates it (hw1f_steps_to): one probe per (S1, dt)
     bool steps_cached = false;
     float steps_S1 = 0.f, steps_dt = 0.f;
@@ -359,9 +374,31 @@ int ensure_windows(hw1f_engine* e, uint32_t L_log2, uint32_t hi_first, uint32_t 
     return HW1F_OK;
 }
 
-// Prepare a launch over `n_runs` seeds sharing (first_path, n_paths, normal offset).
+ModelDev model_dev(const hw1f_engine* e);
+
+// a launch with (or without) programmatic stream serialisation: the simulation kernels start while the prep_lo_kernel
+// in front of them is still running and wait for it with griddepcontrol.wait (hw1f_kernels_fast.cuh)
+template <class... KArgs, class... Args>
+cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, bool pdl,
+                     Args&&... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);
+}
+
+// Prepare a launch over `n_runs` seeds sharing (first_path, n_paths, normal offset).  `job` (optional): bond plans
+// computed by an extra block of the same prep_lo_kernel launch.
 int prepare_launch(hw1f_engine* e, const uint64_t* seeds, int n_runs, uint64_t first_path, uint64_t n_paths,
-                   uint64_t normal_offset, Launch* L)
+                   uint64_t normal_offset, Launch* L, const PlanJob* job = nullptr)
 {
     HW_REQUIRE(e, n_runs >= 1 && n_runs <= kMaxRuns, "n_runs must be in [1,32]");
     HW_REQUIRE(e, n_paths >= 1, "n_paths must be >= 1");
@@ -394,7 +431,11 @@ int prepare_launch(hw1f_engine* e, const uint64_t* seeds, int n_runs, uint64_t f
 
     const unsigned long long total_warps = (unsigned long long)n_runs * Lsz;
     const unsigned prep_blocks = (unsigned)((total_warps + 7) / 8);
-    prep_lo_kernel<<<prep_blocks, 256, 0, e->stream>>>(L->seeds, n_runs, L_log2, e->d_Jpow2.p, e->d_U.p);
+    PlanJob no_job{};
+    if (job) HW_CUDA(e, e->d_plans.ensure(4));
+    // + 1: the plan block
+    prep_lo_kernel<<<prep_blocks + 1, 256, 0, e->stream>>>(L->seeds, n_runs, L_log2, e->d_Jpow2.p, e->d_U.p, model_dev(e),
+                                                          job ? *job : no_job);
     HW_TRY(check_launch(e, "prep_lo_kernel"));
 
     StreamGeom& g = L->g;
@@ -442,30 +483,15 @@ int resolve_steps(hw1f_engine* e, float S1, int32_t n_in, int32_t* n_out)
     return HW1F_OK;
 }
 
-// bond plans for up to two scenarios on DEVICE-resident market curves (the recalibrated FD's own curves);
-// market set s at d_mkt[2s], d_mkt[2s+1]
-int launch_plans(hw1f_engine* e, const ScenDev* sc, int n_scen, float S1, float S2)
-{
-    const int n = e->p.n_mat;
-    HW_CUDA(e, e->d_plans.ensure(kMaxScen));
-    const float* P0 = e->d_mkt.p;
-    const float* f0 = P0 + n;
-    const float* P1 = P0 + 2 * n;
-    const float* f1 = P0 + 3 * n;
-    bond_plan_kernel<<<1, 32, 0, e->stream>>>(model_dev(e), sc[0], sc[n_scen > 1 ? 1 : 0], n_scen, S1, S2, P0, f0,
-                                              n_scen > 1 ? P1 : P0, n_scen > 1 ? f1 : f0, e->d_plans.p, MktPts{}, 0);
-    return check_launch(e, "bond_plan_kernel");
-}
-
-// bond plans for one or two scenarios priced on HOST-resident market curves: the six values the plan reads travel
-// as kernel arguments -- no market upload, one launch.  Plans go to d_plans[slot0 ..).
-int launch_plans_host(hw1f_engine* e, const ScenDev* sc, int n_scen, float S1, float S2, const float* P_mkt,
+// ---- bond plans: path-independent part of P(S1,S2), computed on the device as a side job --------
+// plans for up to three scenarios priced on HOST-resident market curves: the six values a plan reads travel as kernel
+// arguments (no market upload).  Plans go to d_plans[slot0 ..).
+PlanJob plan_job_host(hw1f_engine* e, const ScenDev* sc, int n_scen, float S1, float S2, const float* P_mkt,
                       const float* f_mkt, int slot0 = 0)
 {
     const int n = e->p.n_mat;
-    HW_CUDA(e, e->d_plans.ensure(4));
     const ModelDev md = model_dev(e);
-    MktPts pts{};
+    PlanJob job{};
     auto pick = [&](const float* data, float T, float out[2]) {
         const float prod = T * md.inv_spacing;           // IEEE single multiply, like mul_() on the device
         int idx = (prod >= (float)n) ? n : (int)prod;    // (int): truncation = __float2int_rz
@@ -474,12 +500,41 @@ int launch_plans_host(hw1f_engine* e, const ScenDev* sc, int n_scen, float S1, f
         else { out[0] = data[idx]; out[1] = data[idx + 1]; }
         return idx;
     };
-    pts.idx_S2 = pick(P_mkt, S2, pts.P_S2);
-    pts.idx_S1 = pick(P_mkt, S1, pts.P_S1);
-    pick(f_mkt, S1, pts.f_S1);
-    bond_plan_kernel<<<1, 32, 0, e->stream>>>(md, sc[0], sc[n_scen > 1 ? 1 : 0], n_scen, S1, S2, nullptr, nullptr, nullptr,
-                                              nullptr, e->d_plans.p + slot0, pts, 1);
-    return check_launch(e, "bond_plan_kernel");
+    job.pts.idx_S2 = pick(P_mkt, S2, job.pts.P_S2);
+    job.pts.idx_S1 = pick(P_mkt, S1, job.pts.P_S1);
+    pick(f_mkt, S1, job.pts.f_S1);
+    job.use_pts = 1;
+    job.n_scen = n_scen;
+    for (int s = 0; s < n_scen; ++s) { job.sigma[s] = sc[s].sigma; job.sig_st[s] = sc[s].sig_st; }
+    job.S1 = S1;
+    job.S2 = S2;
+    job.plans = e->d_plans.p + slot0;   // d_plans holds 4 entries from engine creation on
+    return job;
+}
+
+// plans for two scenarios on DEVICE-resident market curves (the recalibrated FD's own curves): market set s at
+// d_mkt[2s], d_mkt[2s+1]
+PlanJob plan_job_dev(hw1f_engine* e, const ScenDev* sc, int n_scen, float S1, float S2)
+{
+    const int n = e->p.n_mat;
+    PlanJob job{};
+    job.n_scen = n_scen;
+    for (int s = 0; s < n_scen; ++s) { job.sigma[s] = sc[s].sigma; job.sig_st[s] = sc[s].sig_st; }
+    job.S1 = S1;
+    job.S2 = S2;
+    job.use_pts = 0;
+    for (int s = 0; s < 2; ++s) {
+        job.P_mkt[s] = e->d_mkt.p + 2 * (size_t)(n_scen > 1 ? s : 0) * n;
+        job.f_mkt[s] = job.P_mkt[s] + n;
+    }
+    job.plans = e->d_plans.p;
+    return job;
+}
+
+int launch_plan_job(hw1f_engine* e, const PlanJob& job)
+{
+    plan_job_kernel<<<1, 32, 0, e->stream>>>(model_dev(e), job);
+    return check_launch(e, "plan_job_kernel");
 }
 
 ScenDev scen_dev(const hw1f_engine* e, float sigma, float sig_st, int drift_slot)
@@ -554,10 +609,90 @@ cudaError_t opt_in(K kernel, size_t bytes)
     return cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
 }
 
+// ---- what happens after the block partials exist (hw1f_tail.cuh) ---------------------------------
+// Finish says what the last block of a simulation launch does beyond storing the device moment vector; in
+// reference-order mode (separate reduction kernels) the same steps run as tail_publish_kernel.
+struct Finish {
+    double* host_mom = nullptr;     // copy of the moment vector in mapped pinned host memory
+    bool exchange = false;          // all-reduce with the attached peers (hw1f_comm_attach)
+    bool epi = false;               // curve epilogue: P, f (P_se) of every curve scenario
+    uint64_t n_total = 0;           //   subsequences over all ranks
+    float* dev_curve = nullptr;     //   [ncur][2][n_mat] on the device
+    float* host_curve = nullptr;    //   [ncur][3][n_mat] in mapped pinned host memory
+    PlanJob plan{};                 // bond plans on dev_curve afterwards
+};
+
+// result areas in mapped pinned host memory: area k = [res_doubles doubles][res_floats floats]
+double* res_mom(const hw1f_engine* e, int area) { return reinterpret_cast<double*>(e->h_res + (size_t)area * e->res_area_bytes); }
+float* res_curve(const hw1f_engine* e, int area)
+{
+    return reinterpret_cast<float*>(e->h_res + (size_t)area * e->res_area_bytes + e->res_doubles * sizeof(double));
+}
+
+int make_tail(hw1f_engine* e, int n_runs, unsigned grid_x, uint64_t n_local, int nq, int ncur, const float* c0,
+              const float* c1, float scale, double* d_moments, int out_stride, int n_ext_out, const Finish& fin, TailArgs* t)
+{
+    const unsigned n_groups = (grid_x + kTailGroup - 1) / kTailGroup;
+    HW_REQUIRE(e, n_runs <= kTailCounters, "too many runs for the ticket counters");
+    HW_CUDA(e, e->d_gpart.ensure((size_t)n_runs * n_groups * nq));
+    memset(t, 0, sizeof(*t));
+    t->counters = e->d_tail_cnt.p;
+    t->gpart = e->d_gpart.p;
+    t->moments = d_moments;
+    t->host_mom = fin.host_mom;
+    t->out_stride = out_stride;
+    t->n_ext_out = n_ext_out;
+    t->ncur = ncur;
+    t->n_mat = e->p.n_mat;
+    t->center0 = c0;
+    t->center1 = c1;
+    t->center_scale = scale;
+    t->n_local = n_local;
+    if (fin.exchange && e->comm_on) {
+        HW_REQUIRE(e, n_runs == 1, "the peer exchange works on single-run launches");
+        HW_REQUIRE(e, ncur * 2 * e->p.n_mat + n_ext_out <= kCommMaxCount, "moment vector too long for the peer mailboxes");
+        t->comm = e->comm;
+        t->epoch = ++*e->comm_epoch;
+    }
+    t->epi = fin.epi ? 1 : 0;
+    t->n_total = fin.n_total;
+    t->inv_dT = 1.0f / e->spacing;   // host division, src/1:76
+    t->dev_curve = fin.dev_curve;
+    t->host_curve = fin.host_curve;
+    t->plan = fin.plan;
+    return HW1F_OK;
+}
+
+// the publication step alone (the *_finish entry points: the vector comes back from an external all-reduce)
+int publish(hw1f_engine* e, int n_runs, int ncur, double* d_moments, int out_stride, int n_ext_out, const Finish& fin)
+{
+    if (!fin.host_mom && !(fin.exchange && e->comm_on) && !fin.epi) return HW1F_OK;
+    TailArgs t;
+    HW_TRY(make_tail(e, n_runs, 1, 0, 1, ncur, nullptr, nullptr, 0.f, d_moments, out_stride, n_ext_out, fin, &t));
+    tail_publish_kernel<<<n_runs, 256, (size_t)e->p.n_mat * sizeof(float), e->stream>>>(t, model_dev(e), ncur * 2 * e->p.n_mat);
+    return check_launch(e, "tail_publish_kernel");
+}
+
+// everything behind a simulation launch in ONE kernel (hw1f_tail.cuh), launched with programmatic stream serialisation:
+// its blocks are resident, parked in griddepcontrol.wait, when the last simulation block retires
+int launch_tail(hw1f_engine* e, const Launch& L, uint64_t n_local, int nq, int ncur, const float* c0, const float* c1,
+                float scale, double* d_moments, int out_stride, int n_ext_out, const Finish& fin)
+{
+    TailArgs ta;
+    HW_TRY(make_tail(e, L.n_runs, L.grid_x, n_local, nq, ncur, c0, c1, scale, d_moments, out_stride, n_ext_out, fin, &ta));
+    const unsigned n_groups = (L.grid_x + kTailGroup - 1) / kTailGroup;
+    const size_t smem = tail_smem_bytes(nq, e->p.n_mat);
+    HW_REQUIRE(e, smem <= 48 * 1024, "moment vector too long for the tail kernel's shared memory");
+    HW_CUDA(e, launch_k(tail_kernel, dim3(n_groups, L.n_runs), dim3(kTailThreads), smem, e->stream, true, ta, model_dev(e),
+                        (const double*)e->d_partials.p, (int)L.grid_x, nq, ncur * 2 * e->p.n_mat));
+    return check_launch(e, "tail_kernel");
+}
+
 // ---- Q1 launch: sums for NSCEN scenarios into d_moments[n_runs][nscen*2*n_mat] -----------------
 // dump_steps > 0 (decomposed mode, two scenarios, dump_steps on a save point): the kernel also stores the noise
 // state of every subsequence at that step into e->d_state (see fast_kernel DUMP)
-int launch_curve(hw1f_engine* e, const Launch& L, const ScenDev* sc, int nscen, double* d_moments, int dump_steps = 0)
+int launch_curve(hw1f_engine* e, const Launch& L, const ScenDev* sc, int nscen, double* d_moments, int dump_steps = 0,
+                 const Finish& fin = Finish())
 {
     const int nm = e->p.n_mat, nq = nscen * 2 * nm;
     HW_CUDA(e, e->d_partials.ensure((size_t)L.n_runs * L.grid_x * nq));
@@ -567,25 +702,23 @@ int launch_curve(hw1f_engine* e, const Launch& L, const ScenDev* sc, int nscen, 
         const FastScen c0 = fast_scen(e, sc[0].sig_st, slot0, 0), c1 = fast_scen(e, sc[nscen > 1 ? 1 : 0].sig_st, slot1, 0);
         const FastTangent tg{0.f, 0.f};
         const size_t smem = smem_fast(e, nscen);
+        const ModelDev md = model_dev(e);
         if (nscen == 1) {
             HW_TRY(set_smem(e, fast_kernel<1, 0, 0>, smem));
-            fast_kernel<1, 0, 0><<<grid, kThreads, smem, e->stream>>>(L.g, L.seeds, model_dev(e), c0, c1, c0, c0, c0, tg,
-                                                                     e->d_plans.p, 0, 0, 0.f, e->d_partials.p, nullptr);
+            HW_CUDA(e, launch_k(fast_kernel<1, 0, 0>, grid, kThreads, smem, e->stream, true, L.g, L.seeds, md, c0, c1, c0, c0,
+                                c0, tg, e->d_plans.p, 0, 0, 0.f, e->d_partials.p, (float2*)nullptr));
         } else if (dump_steps > 0) {
             HW_CUDA(e, e->d_state.ensure((size_t)L.n_runs * L.g.n_chunks * kChunk));
             HW_TRY(set_smem(e, (fast_kernel<2, 0, 0, 1>), smem));
-            fast_kernel<2, 0, 0, 1><<<grid, kThreads, smem, e->stream>>>(L.g, L.seeds, model_dev(e), c0, c1, c0, c0, c0, tg,
-                                                                        e->d_plans.p, dump_steps, 0, 0.f, e->d_partials.p,
-                                                                        e->d_state.p);
+            HW_CUDA(e, launch_k(fast_kernel<2, 0, 0, 1>, grid, kThreads, smem, e->stream, true, L.g, L.seeds, md, c0, c1, c0,
+                                c0, c0, tg, e->d_plans.p, dump_steps, 0, 0.f, e->d_partials.p, e->d_state.p));
         } else {
             HW_TRY(set_smem(e, fast_kernel<2, 0, 0>, smem));
-            fast_kernel<2, 0, 0><<<grid, kThreads, smem, e->stream>>>(L.g, L.seeds, model_dev(e), c0, c1, c0, c0, c0, tg,
-                                                                     e->d_plans.p, 0, 0, 0.f, e->d_partials.p, nullptr);
+            HW_CUDA(e, launch_k(fast_kernel<2, 0, 0>, grid, kThreads, smem, e->stream, true, L.g, L.seeds, md, c0, c1, c0, c0,
+                                c0, tg, e->d_plans.p, 0, 0, 0.f, e->d_partials.p, (float2*)nullptr));
         }
         HW_TRY(check_launch(e, "fast_kernel<curve>"));
-        reduce_curve_kernel<<<dim3(nm, L.n_runs * nscen), 256, 0, e->stream>>>(
-            e->d_partials.p, (int)L.grid_x, nq, nscen, nm, c0.emI, c1.emI, 2.0f, L.g.n_paths, d_moments, nq);
-        return check_launch(e, "reduce_curve_kernel");
+        return launch_tail(e, L, L.g.n_paths, nq, nscen, c0.emI, c1.emI, 2.0f, d_moments, nq, 0, fin);
     }
     const size_t smem = smem_curve(e, nscen);
     if (nscen == 1) {
@@ -598,14 +731,11 @@ int launch_curve(hw1f_engine* e, const Launch& L, const ScenDev* sc, int nscen, 
                                                                   e->d_partials.p);
     }
     HW_TRY(check_launch(e, "bond_curve_kernel"));
-    reduce_curve_kernel<<<dim3(nm, L.n_runs * nscen), 256, 0, e->stream>>>(
-        e->d_partials.p, (int)L.grid_x, nq, nscen, nm, sc[0].center, sc[nscen > 1 ? 1 : 0].center, 1.0f, L.g.n_paths,
-        d_moments, nq);
-    return check_launch(e, "reduce_curve_kernel");
+    return launch_tail(e, L, L.g.n_paths, nq, nscen, sc[0].center, sc[nscen > 1 ? 1 : 0].center, 1.0f, d_moments, nq, 0, fin);
 }
 
 int launch_zbc(hw1f_engine* e, const Launch& L, const ScenDev* sc, int nscen, int n_steps_S1, float K,
-               double* d_moments)
+               double* d_moments, const Finish& fin = Finish())
 {
     const int nq = nscen * 5;
     HW_CUDA(e, e->d_partials.ensure((size_t)L.n_runs * L.grid_x * nq));
@@ -615,47 +745,51 @@ int launch_zbc(hw1f_engine* e, const Launch& L, const ScenDev* sc, int nscen, in
         const FastScen z1 = fast_scen(e, sc[nscen > 1 ? 1 : 0].sig_st, drift_slot_of(e, sc[nscen > 1 ? 1 : 0]), n_steps_S1);
         const FastTangent tg{0.f, 0.f};
         const size_t smemf = smem_fast(e, 0);
+        const ModelDev md = model_dev(e);
         if (nscen == 1) {
             HW_TRY(set_smem(e, fast_kernel<0, 1, 0>, smemf));
-            fast_kernel<0, 1, 0><<<grid, kThreads, smemf, e->stream>>>(L.g, L.seeds, model_dev(e), z0, z0, z0, z1, z1, tg,
-                                                                      e->d_plans.p, n_steps_S1, L.lead, K, e->d_partials.p, nullptr);
+            HW_CUDA(e, launch_k(fast_kernel<0, 1, 0>, grid, kThreads, smemf, e->stream, true, L.g, L.seeds, md, z0, z0, z0, z1,
+                                z1, tg, e->d_plans.p, n_steps_S1, L.lead, K, e->d_partials.p, (float2*)nullptr));
         } else {
             HW_TRY(set_smem(e, fast_kernel<0, 2, 0>, smemf));
-            fast_kernel<0, 2, 0><<<grid, kThreads, smemf, e->stream>>>(L.g, L.seeds, model_dev(e), z0, z0, z0, z1, z1, tg,
-                                                                      e->d_plans.p, n_steps_S1, L.lead, K, e->d_partials.p, nullptr);
+            HW_CUDA(e, launch_k(fast_kernel<0, 2, 0>, grid, kThreads, smemf, e->stream, true, L.g, L.seeds, md, z0, z0, z0, z1,
+                                z1, tg, e->d_plans.p, n_steps_S1, L.lead, K, e->d_partials.p, (float2*)nullptr));
         }
         HW_TRY(check_launch(e, "fast_kernel<zbc>"));
-        return reduce_to(e, L.n_runs, L.grid_x, nq, d_moments);
-    }
-    const size_t smem = (size_t)kWinWords * 4 + (size_t)nscen * ((n_steps_S1 + 1) / 2 + 1) * sizeof(float4);
-    if (nscen == 1) {
-        HW_TRY(set_smem(e, zbc_kernel<1>, smem));
-        zbc_kernel<1><<<grid, kThreads, smem, e->stream>>>(L.g, L.seeds, model_dev(e), sc[0], sc[0], e->d_plans.p,
-                                                           n_steps_S1, L.lead, K, e->d_partials.p);
     } else {
-        HW_TRY(set_smem(e, zbc_kernel<2>, smem));
-        zbc_kernel<2><<<grid, kThreads, smem, e->stream>>>(L.g, L.seeds, model_dev(e), sc[0], sc[1], e->d_plans.p,
-                                                           n_steps_S1, L.lead, K, e->d_partials.p);
+        const size_t smem = (size_t)kWinWords * 4 + (size_t)nscen * ((n_steps_S1 + 1) / 2 + 1) * sizeof(float4);
+        if (nscen == 1) {
+            HW_TRY(set_smem(e, zbc_kernel<1>, smem));
+            zbc_kernel<1><<<grid, kThreads, smem, e->stream>>>(L.g, L.seeds, model_dev(e), sc[0], sc[0], e->d_plans.p,
+                                                               n_steps_S1, L.lead, K, e->d_partials.p);
+        } else {
+            HW_TRY(set_smem(e, zbc_kernel<2>, smem));
+            zbc_kernel<2><<<grid, kThreads, smem, e->stream>>>(L.g, L.seeds, model_dev(e), sc[0], sc[1], e->d_plans.p,
+                                                               n_steps_S1, L.lead, K, e->d_partials.p);
+        }
+        HW_TRY(check_launch(e, "zbc_kernel"));
     }
-    HW_TRY(check_launch(e, "zbc_kernel"));
-    return reduce_to(e, L.n_runs, L.grid_x, nq, d_moments);
+    return launch_tail(e, L, L.g.n_paths, nq, 0, nullptr, nullptr, 0.f, d_moments, nq, nq, fin);
 }
 
 // the two ZBC scenarios evaluated on the noise state a preceding launch_curve(.., dump_steps = n_steps_S1) left in
 // e->d_state: same moments as launch_zbc on the same normals, without simulating them again
-int launch_zbc_from_state(hw1f_engine* e, const Launch& L, const ScenDev* sc, int n_steps_S1, float K, double* d_moments)
+int launch_zbc_from_state(hw1f_engine* e, const Launch& L, const ScenDev* sc, int n_steps_S1, float K, double* d_moments,
+                          const Finish& fin = Finish())
 {
     const int nq = 10;
     HW_CUDA(e, e->d_partials.ensure((size_t)L.n_runs * L.grid_x * nq));
     const FastScen z0 = fast_scen(e, sc[0].sig_st, drift_slot_of(e, sc[0]), n_steps_S1);
     const FastScen z1 = fast_scen(e, sc[1].sig_st, drift_slot_of(e, sc[1]), n_steps_S1);
+    // behind the curve launch's tail kernel (which wrote the recalibrated curves' bond plans): ordinary stream order
     zbc_from_state_kernel<2><<<dim3(L.grid_x, L.n_runs), kThreads, 0, e->stream>>>(L.g, z0, z1, e->d_plans.p, K, e->d_state.p,
                                                                                   e->d_partials.p);
     HW_TRY(check_launch(e, "zbc_from_state_kernel"));
-    return reduce_to(e, L.n_runs, L.grid_x, nq, d_moments);
+    return launch_tail(e, L, L.g.n_paths, nq, 0, nullptr, nullptr, 0.f, d_moments, nq, nq, fin);
 }
 
-int launch_pathwise(hw1f_engine* e, const Launch& L, const ScenDev& sc, int n_steps_S1, float K, double* d_moments)
+int launch_pathwise(hw1f_engine* e, const Launch& L, const ScenDev& sc, int n_steps_S1, float K, double* d_moments,
+                    const Finish& fin = Finish())
 {
     HW_CUDA(e, e->d_partials.ensure((size_t)L.n_runs * L.grid_x * 3));
     if (e->mode == HW1F_MODE_DECOMPOSED) {
@@ -663,10 +797,12 @@ int launch_pathwise(hw1f_engine* e, const Launch& L, const ScenDev& sc, int n_st
         const FastTangent tg = fast_tangent(e, n_steps_S1);
         const size_t smemf = smem_fast(e, 0);
         HW_TRY(set_smem(e, fast_kernel<0, 0, 1>, smemf));
-        fast_kernel<0, 0, 1><<<dim3(L.grid_x, L.n_runs), kThreads, smemf, e->stream>>>(
-            L.g, L.seeds, model_dev(e), z0, z0, z0, z0, z0, tg, e->d_plans.p, n_steps_S1, L.lead, K, e->d_partials.p, nullptr);
+        HW_CUDA(e, launch_k(fast_kernel<0, 0, 1>, dim3(L.grid_x, L.n_runs), kThreads, smemf, e->stream, true, L.g, L.seeds,
+                            model_dev(e), z0, z0, z0, z0, z0, tg, e->d_plans.p, n_steps_S1, L.lead, K, e->d_partials.p,
+                            (float2*)nullptr));
         HW_TRY(check_launch(e, "fast_kernel<pathwise>"));
-        return reduce_range(e, L.n_runs, L.grid_x, 3, 0, 2, d_moments, 2);
+        // the kernel keeps a third sum (for the fused form); the entry points emit sum v, sum v^2
+        return launch_tail(e, L, L.g.n_paths, 3, 0, nullptr, nullptr, 0.f, d_moments, 2, 2, fin);
     }
     const size_t smem = (size_t)kWinWords * 4 + (size_t)(n_steps_S1 + 1) * sizeof(float4);
     HW_TRY(set_smem(e, pathwise_kernel, smem));
@@ -674,7 +810,7 @@ int launch_pathwise(hw1f_engine* e, const Launch& L, const ScenDev& sc, int n_st
                                                                             e->d_plans.p, n_steps_S1, L.lead, K,
                                                                             e->d_partials.p);
     HW_TRY(check_launch(e, "pathwise_kernel"));
-    return reduce_to(e, L.n_runs, L.grid_x, 2, d_moments);
+    return launch_tail(e, L, L.g.n_paths, 2, 0, nullptr, nullptr, 0.f, d_moments, 2, 2, fin);
 }
 
 // a moment vector that went through a timed-out peer all-reduce is NaN-poisoned (hw1f_comm.cu)
@@ -763,7 +899,9 @@ int init_kernels(hw1f_engine* e)
     cudaFuncAttributes attr;
     HW_CUDA(e, cudaFuncGetAttributes(&attr, prep_lo_kernel));
     HW_CUDA(e, cudaFuncGetAttributes(&attr, build_hi_kernel));
-    HW_CUDA(e, cudaFuncGetAttributes(&attr, bond_plan_kernel));
+    HW_CUDA(e, cudaFuncGetAttributes(&attr, plan_job_kernel));
+    HW_CUDA(e, cudaFuncGetAttributes(&attr, tail_publish_kernel));
+    HW_CUDA(e, cudaFuncGetAttributes(&attr, tail_kernel));
     HW_CUDA(e, cudaFuncGetAttributes(&attr, reduce_partials_kernel<double>));
     HW_CUDA(e, cudaFuncGetAttributes(&attr, reduce_curve_kernel));
     HW_CUDA(e, cudaFuncGetAttributes(&attr, zbc_from_state_kernel<2>));
@@ -772,6 +910,10 @@ int init_kernels(hw1f_engine* e)
     HW_CUDA(e, cudaFuncGetAttributes(&attr, fused_uncenter_kernel));
     HW_CUDA(e, cudaFuncGetAttributes(&attr, sample_paths_kernel));
     HW_CUDA(e, cudaFuncGetAttributes(&attr, steps_probe_kernel));
+    // ticket counters of the kernel tails (self-resetting: zeroed once), bond plans
+    HW_CUDA(e, e->d_tail_cnt.ensure(kTailCounters));
+    HW_CUDA(e, cudaMemsetAsync(e->d_tail_cnt.p, 0, kTailCounters * sizeof(unsigned), e->stream));
+    HW_CUDA(e, e->d_plans.ensure(4));
     return ensure_tables(e);
 }
 
@@ -880,6 +1022,8 @@ int hw1f_engine_destroy(hw1f_engine* e)
     e->d_out.release(); e->d_int.release();
     e->d_model.release();
     e->d_fd.release();
+    e->d_tail_cnt.release(); e->d_gpart.release();
+    if (e->h_res) cudaFreeHost(e->h_res);
     if (e->h_model) cudaFreeHost(e->h_model);
     if (e->h_fd) cudaFreeHost(e->h_fd);
     if (e->ev_fd) cudaEventDestroy(e->ev_fd);
@@ -1006,6 +1150,19 @@ int hw1f_set_model(hw1f_engine* e, const hw1f_params* p)
         e->fd_cached = false;      // the bumped-sigma tables and the step probe depend on the model
         e->steps_cached = false;
     }
+    {   // result areas: the longest moment vector (two curve scenarios + extras) and P, f, P_se of two curves
+        const size_t nd = (4 * (size_t)nm + 64 > 512) ? 4 * (size_t)nm + 64 : 512, nf = 6 * (size_t)nm;
+        const size_t bytes = align(nd * sizeof(double) + nf * sizeof(float));
+        if (bytes != e->res_area_bytes) {
+            HW_CUDA(e, cudaStreamSynchronize(e->stream));
+            if (e->h_res) cudaFreeHost(e->h_res);
+            e->h_res = nullptr;
+            e->res_area_bytes = 0;
+            HW_CUDA(e, cudaHostAlloc((void**)&e->h_res, kResAreas * bytes, cudaHostAllocMapped));
+            e->res_area_bytes = bytes;
+            e->res_doubles = nd;
+        }
+    }
     e->has_model = true;
     // compute_constants(): ONE host->device copy of the model tables (every call, like the reference's
     // cudaMemcpyToSymbol sequence; only the host-side table building is cached)
@@ -1102,11 +1259,15 @@ int hw1f_rng_prepare(hw1f_engine* e, const hw1f_rng* rng)
 }
 
 // ---- Q1 ----------------------------------------------------------------------------------------
-int hw1f_bond_curve_moments(hw1f_engine* e, hw1f_rng* rng, double* d_moments)
+// stream-ordered wait + the host's view of a result area
+static int wait_results(hw1f_engine* e)
 {
-    HW_TRY(require_model(e));
-    if (!rng || !d_moments) return HW1F_ERR_INVALID;
-    HW_CUDA(e, cudaSetDevice(e->device));
+    HW_CUDA(e, cudaStreamSynchronize(e->stream));
+    return HW1F_OK;
+}
+
+static int curve_run(hw1f_engine* e, hw1f_rng* rng, double* d_moments, const Finish& fin)
+{
     if ((rng->offset & 1) || (e->stride & 1)) {
         e->err = "bond curve needs an even normal offset and an even save stride";
         return HW1F_ERR_UNSUPPORTED;
@@ -1114,9 +1275,34 @@ int hw1f_bond_curve_moments(hw1f_engine* e, hw1f_rng* rng, double* d_moments)
     Launch L;
     HW_TRY(prepare_launch(e, &rng->seed, 1, rng->first_path, rng->n_paths, rng->offset, &L));
     const ScenDev sc = scen_dev(e, e->p.sigma, e->sig_st, 0);
-    HW_TRY(launch_curve(e, L, &sc, 1, d_moments));
+    HW_TRY(launch_curve(e, L, &sc, 1, d_moments, 0, fin));
     rng->offset += (uint64_t)e->p.n_steps;
     return HW1F_OK;
+}
+
+static int read_curve(hw1f_engine* e, int area, int scen, float* P, float* f, float* P_se)
+{
+    const int n = e->p.n_mat;
+    const float* h = res_curve(e, area) + (size_t)scen * 3 * n;
+    for (int k = 0; k < n; ++k)
+        if (!std::isfinite(h[k])) {
+            e->err = "moment vector is not finite (a peer all-reduce timed out, see hw1f_comm_timeouts)";
+            return HW1F_ERR_COMM;
+        }
+    memcpy(P, h, n * sizeof(float));
+    memcpy(f, h + n, n * sizeof(float));
+    if (P_se) memcpy(P_se, h + 2 * n, n * sizeof(float));
+    return HW1F_OK;
+}
+
+int hw1f_bond_curve_moments(hw1f_engine* e, hw1f_rng* rng, double* d_moments)
+{
+    HW_TRY(require_model(e));
+    if (!rng || !d_moments) return HW1F_ERR_INVALID;
+    HW_CUDA(e, cudaSetDevice(e->device));
+    Finish fin;
+    fin.exchange = true;   // with peers attached (hw1f_comm_attach) the last block all-reduces the vector itself
+    return curve_run(e, rng, d_moments, fin);
 }
 
 int hw1f_bond_curve_finish(hw1f_engine* e, const double* d_moments, uint64_t n_paths_total, float* P, float* f,
@@ -1126,39 +1312,33 @@ int hw1f_bond_curve_finish(hw1f_engine* e, const double* d_moments, uint64_t n_p
     if (!d_moments || !P || !f) return HW1F_ERR_INVALID;
     HW_REQUIRE(e, n_paths_total >= 1 && n_paths_total < (1ull << 40), "n_paths_total outside [1, 2^40)");
     HW_CUDA(e, cudaSetDevice(e->device));
-    const int n = e->p.n_mat;
-    HW_CUDA(e, e->d_out.ensure(4 * (size_t)n));
-    float* dP = e->d_out.p;
-    float* df = dP + n;
-    float* dse = dP + 2 * n;
-    const float inv_dT = 1.0f / e->spacing;   // host division, src/1:76
-    curve_epilogue_kernel<<<1, ((n + 31) / 32) * 32, n * sizeof(float), e->stream>>>(d_moments, n, n_paths_total,
-                                                                                    inv_dT, dP, df, dse);
-    HW_TRY(check_launch(e, "curve_epilogue_kernel"));
-    std::vector<float> host(3 * (size_t)n);
-    HW_TRY(download(e, host.data(), dP, host.size() * sizeof(float)));
-    for (int k = 0; k < n; ++k)
-        if (!std::isfinite(host[k])) {
-            e->err = "moment vector is not finite (a peer all-reduce timed out, see hw1f_comm_timeouts)";
-            return HW1F_ERR_COMM;
-        }
-    memcpy(P, host.data(), n * sizeof(float));
-    memcpy(f, host.data() + n, n * sizeof(float));
-    if (P_se) memcpy(P_se, host.data() + 2 * n, n * sizeof(float));
-    return HW1F_OK;
+    Finish fin;
+    fin.epi = true;
+    fin.n_total = n_paths_total;
+    fin.host_curve = res_curve(e, 0);
+    HW_TRY(publish(e, 1, 1, const_cast<double*>(d_moments), 2 * e->p.n_mat, 0, fin));
+    HW_TRY(wait_results(e));
+    return read_curve(e, 0, 0, P, f, P_se);
 }
 
 int hw1f_bond_curve(hw1f_engine* e, hw1f_rng* rng, float* P, float* f, float* P_se, float* sim_ms)
 {
     HW_TRY(require_model(e));
-    if (!rng) return HW1F_ERR_INVALID;
+    if (!rng || !P || !f) return HW1F_ERR_INVALID;
     HW_CUDA(e, cudaSetDevice(e->device));
     HW_CUDA(e, e->d_moments.ensure(4 * (size_t)e->p.n_mat * kMaxRuns));
     HW_TRY(warm_geometry(e, rng));
-    HW_CUDA(e, cudaEventRecord(e->ev0, e->stream));
-    HW_TRY(hw1f_bond_curve_moments(e, rng, e->d_moments.p));
-    HW_CUDA(e, cudaEventRecord(e->ev1, e->stream));
-    HW_TRY(hw1f_bond_curve_finish(e, e->d_moments.p, rng->n_paths, P, f, P_se));
+    // one jump-table launch and ONE simulation launch whose last block reduces, finalises and stores P, f, P_se into
+    // mapped pinned host memory; the host waits for the stream
+    Finish fin;
+    fin.epi = true;
+    fin.n_total = rng->n_paths;
+    fin.host_curve = res_curve(e, 0);
+    if (sim_ms) HW_CUDA(e, cudaEventRecord(e->ev0, e->stream));
+    HW_TRY(curve_run(e, rng, e->d_moments.p, fin));
+    if (sim_ms) HW_CUDA(e, cudaEventRecord(e->ev1, e->stream));
+    HW_TRY(wait_results(e));
+    HW_TRY(read_curve(e, 0, 0, P, f, P_se));
     if (sim_ms) HW_CUDA(e, cudaEventElapsedTime(sim_ms, e->ev0, e->ev1));
     return HW1F_OK;
 }
@@ -1186,6 +1366,19 @@ int hw1f_theta_calibrate(hw1f_engine* e, const float* f, float* theta_rec, float
 }
 
 // ---- Q2b ----------------------------------------------------------------------------------------
+static int zbc_run(hw1f_engine* e, hw1f_rng* rng, float S1, float S2, float K, const float* P_mkt, const float* f_mkt,
+                   int32_t n, double* d_moments, const Finish& fin)
+{
+    const ScenDev sc = scen_dev(e, e->p.sigma, e->sig_st, 0);
+    // the bond plan rides on the jump-table launch (its extra block)
+    const PlanJob job = plan_job_host(e, &sc, 1, S1, S2, P_mkt, f_mkt);
+    Launch L;
+    HW_TRY(prepare_launch(e, &rng->seed, 1, rng->first_path, rng->n_paths, rng->offset, &L, &job));
+    HW_TRY(launch_zbc(e, L, &sc, 1, n, K, d_moments, fin));
+    rng->offset += (uint64_t)n;
+    return HW1F_OK;
+}
+
 int hw1f_zbc_cv_moments(hw1f_engine* e, hw1f_rng* rng, float S1, float S2, float K, const float* P_mkt,
                         const float* f_mkt, int32_t n_steps_S1, double* d_moments)
 {
@@ -1194,13 +1387,9 @@ int hw1f_zbc_cv_moments(hw1f_engine* e, hw1f_rng* rng, float S1, float S2, float
     HW_CUDA(e, cudaSetDevice(e->device));
     int32_t n = 0;
     HW_TRY(resolve_steps(e, S1, n_steps_S1, &n));
-    const ScenDev sc = scen_dev(e, e->p.sigma, e->sig_st, 0);
-    Launch L;   // the per-launch jump table first: the plan launch is enqueued while it runs
-    HW_TRY(prepare_launch(e, &rng->seed, 1, rng->first_path, rng->n_paths, rng->offset, &L));
-    HW_TRY(launch_plans_host(e, &sc, 1, S1, S2, P_mkt, f_mkt));
-    HW_TRY(launch_zbc(e, L, &sc, 1, n, K, d_moments));
-    rng->offset += (uint64_t)n;
-    return HW1F_OK;
+    Finish fin;
+    fin.exchange = true;
+    return zbc_run(e, rng, S1, S2, K, P_mkt, f_mkt, n, d_moments, fin);
 }
 
 int hw1f_zbc_cv_finish(hw1f_engine* e, const double* d_moments, uint64_t n_paths_total, float P0S2,
@@ -1221,18 +1410,22 @@ int hw1f_zbc_cv(hw1f_engine* e, hw1f_rng* rng, float S1, float S2, float K, cons
                 int32_t n_steps_S1, hw1f_zbc_result* out, float* sim_ms)
 {
     HW_TRY(require_model(e));
-    if (!rng || !out || !P_mkt) return HW1F_ERR_INVALID;
+    if (!rng || !out || !P_mkt || !f_mkt) return HW1F_ERR_INVALID;
     HW_CUDA(e, cudaSetDevice(e->device));
     int32_t n = 0;
     HW_TRY(resolve_steps(e, S1, n_steps_S1, &n));
     HW_CUDA(e, e->d_moments.ensure(4 * (size_t)e->p.n_mat * kMaxRuns));
     HW_TRY(warm_geometry(e, rng));
-    HW_CUDA(e, cudaEventRecord(e->ev0, e->stream));
-    HW_TRY(hw1f_zbc_cv_moments(e, rng, S1, S2, K, P_mkt, f_mkt, n, e->d_moments.p));
-    HW_CUDA(e, cudaEventRecord(e->ev1, e->stream));
-    out->n_steps_S1 = n;
-    HW_TRY(hw1f_zbc_cv_finish(e, e->d_moments.p, rng->n_paths, P_mkt[e->p.n_mat - 1], out));
-    out->n_steps_S1 = n;
+    Finish fin;
+    fin.host_mom = res_mom(e, 0);
+    if (sim_ms) HW_CUDA(e, cudaEventRecord(e->ev0, e->stream));
+    HW_TRY(zbc_run(e, rng, S1, S2, K, P_mkt, f_mkt, n, e->d_moments.p, fin));
+    if (sim_ms) HW_CUDA(e, cudaEventRecord(e->ev1, e->stream));
+    HW_TRY(wait_results(e));
+    double mom[5];
+    memcpy(mom, res_mom(e, 0), sizeof(mom));
+    HW_TRY(require_finite(e, mom, 5));
+    zbc_algebra(mom, rng->n_paths, P_mkt[e->p.n_mat - 1], n, out);
     if (sim_ms) HW_CUDA(e, cudaEventElapsedTime(sim_ms, e->ev0, e->ev1));
     return HW1F_OK;
 }
@@ -1249,7 +1442,7 @@ int hw1f_zbc_cv_batch(hw1f_engine* e, const uint64_t* seeds, int32_t n_runs, uin
     HW_TRY(resolve_steps(e, S1, n_steps_S1, &n));
     HW_CUDA(e, e->d_moments.ensure(4 * (size_t)e->p.n_mat * kMaxRuns));
     const ScenDev sc = scen_dev(e, e->p.sigma, e->sig_st, 0);
-    HW_TRY(launch_plans_host(e, &sc, 1, S1, S2, P_mkt, f_mkt));
+    const PlanJob job = plan_job_host(e, &sc, 1, S1, S2, P_mkt, f_mkt);
     {
         const hw1f_rng geom{0, 0, n_paths, 0};
         HW_TRY(warm_geometry(e, &geom));
@@ -1258,10 +1451,12 @@ int hw1f_zbc_cv_batch(hw1f_engine* e, const uint64_t* seeds, int32_t n_runs, uin
     for (int32_t done = 0; done < n_runs; done += kMaxRuns) {
         const int nb = (n_runs - done < kMaxRuns) ? (n_runs - done) : kMaxRuns;
         Launch L;
-        HW_TRY(prepare_launch(e, seeds + done, nb, 0, n_paths, 0, &L));
-        HW_TRY(launch_zbc(e, L, &sc, 1, n, K, e->d_moments.p));
-        std::vector<double> mom(5 * (size_t)nb);
-        HW_TRY(download(e, mom.data(), e->d_moments.p, mom.size() * sizeof(double)));
+        HW_TRY(prepare_launch(e, seeds + done, nb, 0, n_paths, 0, &L, &job));
+        Finish fin;
+        fin.host_mom = res_mom(e, 0);   // [run][5]
+        HW_TRY(launch_zbc(e, L, &sc, 1, n, K, e->d_moments.p, fin));
+        HW_TRY(wait_results(e));
+        const double* mom = res_mom(e, 0);
         for (int r = 0; r < nb; ++r) zbc_algebra(&mom[5 * r], n_paths, P_mkt[e->p.n_mat - 1], n, &out[done + r]);
     }
     HW_CUDA(e, cudaEventRecord(e->ev1, e->stream));
@@ -1271,6 +1466,18 @@ int hw1f_zbc_cv_batch(hw1f_engine* e, const uint64_t* seeds, int32_t n_runs, uin
 }
 
 // ---- Q3 ----------------------------------------------------------------------------------------
+static int pathwise_run(hw1f_engine* e, hw1f_rng* rng, float S1, float S2, float K, const float* P_mkt,
+                        const float* f_mkt, int32_t n, double* d_moments, const Finish& fin)
+{
+    const ScenDev sc = scen_dev(e, e->p.sigma, e->sig_st, 0);
+    const PlanJob job = plan_job_host(e, &sc, 1, S1, S2, P_mkt, f_mkt);
+    Launch L;
+    HW_TRY(prepare_launch(e, &rng->seed, 1, rng->first_path, rng->n_paths, rng->offset, &L, &job));
+    HW_TRY(launch_pathwise(e, L, sc, n, K, d_moments, fin));
+    rng->offset += (uint64_t)n;
+    return HW1F_OK;
+}
+
 int hw1f_vega_pathwise_moments(hw1f_engine* e, hw1f_rng* rng, float S1, float S2, float K, const float* P_mkt,
                                const float* f_mkt, int32_t n_steps_S1, double* d_moments)
 {
@@ -1279,36 +1486,41 @@ int hw1f_vega_pathwise_moments(hw1f_engine* e, hw1f_rng* rng, float S1, float S2
     HW_CUDA(e, cudaSetDevice(e->device));
     int32_t n = 0;
     HW_TRY(resolve_steps(e, S1, n_steps_S1, &n));
-    const ScenDev sc = scen_dev(e, e->p.sigma, e->sig_st, 0);
-    Launch L;   // the per-launch jump table first: the plan launch is enqueued while it runs
-    HW_TRY(prepare_launch(e, &rng->seed, 1, rng->first_path, rng->n_paths, rng->offset, &L));
-    HW_TRY(launch_plans_host(e, &sc, 1, S1, S2, P_mkt, f_mkt));
-    HW_TRY(launch_pathwise(e, L, sc, n, K, d_moments));
-    rng->offset += (uint64_t)n;
-    return HW1F_OK;
+    Finish fin;
+    fin.exchange = true;
+    return pathwise_run(e, rng, S1, S2, K, P_mkt, f_mkt, n, d_moments, fin);
+}
+
+static void pathwise_result(const double mom[2], uint64_t n_paths, hw1f_vega_result* out)
+{
+    const double np = (double)n_paths;
+    out->vega_pathwise = (float)mom[0] / (float)n_paths;   // sum / N_PATHS in float, src/3:261
+    out->vega_pathwise_f64 = mom[0] / np;
+    const double var = (np > 1) ? (mom[1] - mom[0] * mom[0] / np) / (np - 1.0) : 0.0;
+    out->vega_pathwise_se = (var > 0) ? sqrt(var / np) : 0.0;
 }
 
 int hw1f_vega_pathwise(hw1f_engine* e, hw1f_rng* rng, float S1, float S2, float K, const float* P_mkt,
                        const float* f_mkt, int32_t n_steps_S1, hw1f_vega_result* out)
 {
     HW_TRY(require_model(e));
-    if (!rng || !out) return HW1F_ERR_INVALID;
+    if (!rng || !out || !P_mkt || !f_mkt) return HW1F_ERR_INVALID;
     HW_CUDA(e, cudaSetDevice(e->device));
     int32_t n = 0;
     HW_TRY(resolve_steps(e, S1, n_steps_S1, &n));
     HW_CUDA(e, e->d_moments.ensure(4 * (size_t)e->p.n_mat * kMaxRuns));
     HW_TRY(warm_geometry(e, rng));
+    Finish fin;
+    fin.host_mom = res_mom(e, 0);
     HW_CUDA(e, cudaEventRecord(e->ev0, e->stream));
-    HW_TRY(hw1f_vega_pathwise_moments(e, rng, S1, S2, K, P_mkt, f_mkt, n, e->d_moments.p));
+    HW_TRY(pathwise_run(e, rng, S1, S2, K, P_mkt, f_mkt, n, e->d_moments.p, fin));
     HW_CUDA(e, cudaEventRecord(e->ev1, e->stream));
+    HW_TRY(wait_results(e));
     double mom[2];
-    HW_TRY(download(e, mom, e->d_moments.p, sizeof(mom)));
-    const double np = (double)rng->n_paths;
+    memcpy(mom, res_mom(e, 0), sizeof(mom));
+    HW_TRY(require_finite(e, mom, 2));
     out->n_steps_S1 = n;
-    out->vega_pathwise = (float)mom[0] / (float)rng->n_paths;   // sum / N_PATHS in float, src/3:261
-    out->vega_pathwise_f64 = mom[0] / np;
-    const double var = (np > 1) ? (mom[1] - mom[0] * mom[0] / np) / (np - 1.0) : 0.0;
-    out->vega_pathwise_se = (var > 0) ? sqrt(var / np) : 0.0;
+    pathwise_result(mom, rng->n_paths, out);
     HW_CUDA(e, cudaEventElapsedTime(&out->ms_pathwise, e->ev0, e->ev1));
     return HW1F_OK;
 }
@@ -1324,7 +1536,7 @@ int hw1f_vega_pathwise_batch(hw1f_engine* e, const uint64_t* seeds, int32_t n_ru
     HW_TRY(resolve_steps(e, S1, n_steps_S1, &n));
     HW_CUDA(e, e->d_moments.ensure(4 * (size_t)e->p.n_mat * kMaxRuns));
     const ScenDev sc = scen_dev(e, e->p.sigma, e->sig_st, 0);
-    HW_TRY(launch_plans_host(e, &sc, 1, S1, S2, P_mkt, f_mkt));
+    const PlanJob job = plan_job_host(e, &sc, 1, S1, S2, P_mkt, f_mkt);
     {
         const hw1f_rng geom{0, 0, n_paths, 0};
         HW_TRY(warm_geometry(e, &geom));
@@ -1333,10 +1545,12 @@ int hw1f_vega_pathwise_batch(hw1f_engine* e, const uint64_t* seeds, int32_t n_ru
     for (int32_t done = 0; done < n_runs; done += kMaxRuns) {
         const int nb = (n_runs - done < kMaxRuns) ? (n_runs - done) : kMaxRuns;
         Launch L;
-        HW_TRY(prepare_launch(e, seeds + done, nb, 0, n_paths, 0, &L));
-        HW_TRY(launch_pathwise(e, L, sc, n, K, e->d_moments.p));
-        std::vector<double> mom(2 * (size_t)nb);
-        HW_TRY(download(e, mom.data(), e->d_moments.p, mom.size() * sizeof(double)));
+        HW_TRY(prepare_launch(e, seeds + done, nb, 0, n_paths, 0, &L, &job));
+        Finish fin;
+        fin.host_mom = res_mom(e, 0);   // [run][2]
+        HW_TRY(launch_pathwise(e, L, sc, n, K, e->d_moments.p, fin));
+        HW_TRY(wait_results(e));
+        const double* mom = res_mom(e, 0);
         for (int r = 0; r < nb; ++r) vega[done + r] = (float)mom[2 * r] / (float)n_paths;   // src/3:561
     }
     HW_CUDA(e, cudaEventRecord(e->ev1, e->stream));
@@ -1353,6 +1567,65 @@ static float zbc_price_cv(const double mom[5], uint64_t n_paths, float P0S2)
     return r.price_cv;
 }
 
+// run_finite_difference, src/3:400-446: sigma -/+ eps, sig_st and shifted drift per bump; both bumps read the same
+// market curves and the same normals.  ONE jump-table launch (with both bond plans) + ONE simulation launch.
+static int fd_run(hw1f_engine* e, hw1f_rng* rng, float S1, float S2, float K, const float* P_mkt, const float* f_mkt,
+                  float eps, int32_t n, double* d_moments, const Finish& fin)
+{
+    const float sig_m = e->p.sigma - eps, sig_p = e->p.sigma + eps;
+    HW_TRY(upload_fd_tables(e, sig_m, sig_p));
+    ScenDev sc[2] = {scen_dev(e, sig_m, host_sig_st(e->p, sig_m), 2), scen_dev(e, sig_p, host_sig_st(e->p, sig_p), 3)};
+    const PlanJob job = plan_job_host(e, sc, 2, S1, S2, P_mkt, f_mkt);
+    Launch L;
+    HW_TRY(prepare_launch(e, &rng->seed, 1, rng->first_path, rng->n_paths, rng->offset, &L, &job));
+    HW_TRY(launch_zbc(e, L, sc, 2, n, K, d_moments, fin));
+    rng->offset += (uint64_t)n;
+    return HW1F_OK;
+}
+
+// run_finite_difference_recalibrated, src/3:484-525.  recompute_market_data (src/3:449-482) re-simulates the curve at
+// sigma -/+ eps with the UNSHIFTED base drift (compute_drift_tables only changes the sensitivity table) on normals
+// [off, off+N_STEPS); the prices then reuse normals [off, off+n) with the recalibrated curves, base drift, bumped
+// sig_st and sigma.  Decomposed mode, S1 on the maturity grid: the curve pass parks every subsequence's noise state at
+// step n, its LAST BLOCK reduces, finalises both curves on the device and computes their bond plans, and the two
+// prices are evaluated from the parked state -- normals [off, off+n) are the first n normals of the curve window, so
+// nothing is simulated twice (8 bytes of state per subsequence: above 2^27 subsequences the second pass is used).
+// res_area: curves (P0S2 of both) and the ten price moments land in that result area.
+static int recal_run(hw1f_engine* e, hw1f_rng* rng, float S1, float S2, float K, float eps, int32_t n, double* d_moments,
+                     int res_area)
+{
+    const float sig_m = e->p.sigma - eps, sig_p = e->p.sigma + eps;
+    ScenDev sc[2] = {scen_dev(e, sig_m, host_sig_st(e->p, sig_m), 0), scen_dev(e, sig_p, host_sig_st(e->p, sig_p), 0)};
+    Launch L;
+    HW_TRY(prepare_launch(e, &rng->seed, 1, rng->first_path, rng->n_paths, rng->offset, &L));
+    const bool one_pass = e->mode == HW1F_MODE_DECOMPOSED && n > 0 && (n % e->stride) == 0 &&
+                          rng->n_paths <= (1ull << 27);
+    Finish fc;
+    fc.epi = true;
+    fc.n_total = rng->n_paths;
+    fc.dev_curve = e->d_mkt.p;
+    fc.host_curve = res_curve(e, res_area);
+    fc.plan = plan_job_dev(e, sc, 2, S1, S2);
+    HW_TRY(launch_curve(e, L, sc, 2, e->d_moments.p, one_pass ? n : 0, fc));
+    Finish fz;
+    fz.host_mom = res_mom(e, res_area);
+    if (one_pass) HW_TRY(launch_zbc_from_state(e, L, sc, n, K, d_moments, fz));
+    else HW_TRY(launch_zbc(e, L, sc, 2, n, K, d_moments, fz));
+    rng->offset += (uint64_t)n;   // the reference leaves d_states after run_zbc_price (src/3:509-510)
+    return HW1F_OK;
+}
+
+static void recal_result(hw1f_engine* e, int res_area, uint64_t n_paths, float eps, hw1f_vega_result* out)
+{
+    const int nm = e->p.n_mat;
+    const double* mom = res_mom(e, res_area);
+    const float* cur = res_curve(e, res_area);
+    const float P0S2[2] = {cur[nm - 1], cur[3 * (size_t)nm + nm - 1]};
+    out->price_minus_recal = zbc_price_cv(mom, n_paths, P0S2[0]);
+    out->price_plus_recal = zbc_price_cv(mom + 5, n_paths, P0S2[1]);
+    out->vega_fd_recal = (out->price_plus_recal - out->price_minus_recal) / (2.0f * eps);   // src/3:513
+}
+
 int hw1f_vega_fd(hw1f_engine* e, hw1f_rng* rng, float S1, float S2, float K, const float* P_mkt, const float* f_mkt,
                  float eps, int32_t n_steps_S1, hw1f_vega_result* out)
 {
@@ -1363,21 +1636,16 @@ int hw1f_vega_fd(hw1f_engine* e, hw1f_rng* rng, float S1, float S2, float K, con
     int32_t n = 0;
     HW_TRY(resolve_steps(e, S1, n_steps_S1, &n));
     HW_CUDA(e, e->d_moments.ensure(4 * (size_t)e->p.n_mat * kMaxRuns));
-    // run_finite_difference, src/3:400-446: sigma -/+ eps, sig_st and shifted drift per bump;
-    // both bumps read the same market curves and the same normals
-    const float sig_m = e->p.sigma - eps, sig_p = e->p.sigma + eps;
-    HW_TRY(upload_fd_tables(e, sig_m, sig_p));
-    ScenDev sc[2] = {scen_dev(e, sig_m, host_sig_st(e->p, sig_m), 2), scen_dev(e, sig_p, host_sig_st(e->p, sig_p), 3)};
     HW_TRY(warm_geometry(e, rng));
+    Finish fin;
+    fin.host_mom = res_mom(e, 0);
     HW_CUDA(e, cudaEventRecord(e->ev0, e->stream));
-    Launch L;
-    HW_TRY(prepare_launch(e, &rng->seed, 1, rng->first_path, rng->n_paths, rng->offset, &L));
-    HW_TRY(launch_plans_host(e, sc, 2, S1, S2, P_mkt, f_mkt));
-    HW_TRY(launch_zbc(e, L, sc, 2, n, K, e->d_moments.p));
+    HW_TRY(fd_run(e, rng, S1, S2, K, P_mkt, f_mkt, eps, n, e->d_moments.p, fin));
     HW_CUDA(e, cudaEventRecord(e->ev1, e->stream));
+    HW_TRY(wait_results(e));
     double mom[10];
-    HW_TRY(download(e, mom, e->d_moments.p, sizeof(mom)));
-    rng->offset += (uint64_t)n;
+    memcpy(mom, res_mom(e, 0), sizeof(mom));
+    HW_TRY(require_finite(e, mom, 10));
     const float P0S2 = P_mkt[e->p.n_mat - 1];
     out->n_steps_S1 = n;
     out->price_minus = zbc_price_cv(mom, rng->n_paths, P0S2);
@@ -1402,46 +1670,15 @@ int hw1f_vega_fd_recalibrated(hw1f_engine* e, hw1f_rng* rng, float S1, float S2,
     HW_TRY(resolve_steps(e, S1, n_steps_S1, &n));
     const int nm = e->p.n_mat;
     HW_CUDA(e, e->d_moments.ensure(4 * (size_t)nm * kMaxRuns));
-    HW_CUDA(e, e->d_out.ensure(4 * (size_t)nm));
     HW_CUDA(e, e->d_mkt.ensure(4 * (size_t)nm));
-    // run_finite_difference_recalibrated, src/3:484-525.  recompute_market_data (src/3:449-482)
-    // re-simulates the curve at sigma -/+ eps with the UNSHIFTED base drift (compute_drift_tables
-    // only changes the sensitivity table) on normals [off, off+N_STEPS); the prices then reuse
-    // normals [off, off+n) with the recalibrated curves, base drift, bumped sig_st and sigma.
-    const float sig_m = e->p.sigma - eps, sig_p = e->p.sigma + eps;
-    ScenDev sc[2] = {scen_dev(e, sig_m, host_sig_st(e->p, sig_m), 0), scen_dev(e, sig_p, host_sig_st(e->p, sig_p), 0)};
     HW_TRY(warm_geometry(e, rng));
     HW_CUDA(e, cudaEventRecord(e->ev0, e->stream));
-    Launch L;
-    HW_TRY(prepare_launch(e, &rng->seed, 1, rng->first_path, rng->n_paths, rng->offset, &L));
-    // decomposed mode, S1 on the maturity grid: the curve pass parks every subsequence's noise state at step n, and
-    // the two prices are evaluated from it once the recalibrated curves exist -- normals [off, off+n) are the first
-    // n normals of the curve window, so nothing is simulated twice.  Otherwise: second pass over [off, off+n).
-    // (8 bytes of parked state per subsequence: above 2^27 subsequences = 1 GB the second pass is used instead)
-    const bool one_pass = e->mode == HW1F_MODE_DECOMPOSED && n > 0 && (n % e->stride) == 0 &&
-                          rng->n_paths <= (1ull << 27);
-    HW_TRY(launch_curve(e, L, sc, 2, e->d_moments.p, one_pass ? n : 0));
-    const float inv_dT = 1.0f / e->spacing;
-    for (int s = 0; s < 2; ++s) {
-        float* dP = e->d_mkt.p + 2 * (size_t)s * nm;
-        curve_epilogue_kernel<<<1, ((nm + 31) / 32) * 32, nm * sizeof(float), e->stream>>>(
-            e->d_moments.p + 2 * (size_t)s * nm, nm, rng->n_paths, inv_dT, dP, dP + nm, nullptr);
-        HW_TRY(check_launch(e, "curve_epilogue_kernel"));
-    }
-    HW_TRY(launch_plans(e, sc, 2, S1, S2));
-    if (one_pass) HW_TRY(launch_zbc_from_state(e, L, sc, n, K, e->d_moments.p));
-    else HW_TRY(launch_zbc(e, L, sc, 2, n, K, e->d_moments.p));
+    HW_TRY(recal_run(e, rng, S1, S2, K, eps, n, e->d_moments.p + 4 * (size_t)nm, 0));
     HW_CUDA(e, cudaEventRecord(e->ev1, e->stream));
-    double mom[10];
-    HW_TRY(download(e, mom, e->d_moments.p, sizeof(mom)));
-    std::vector<float> mk(4 * (size_t)nm);   // both recalibrated curves in one read-back
-    HW_TRY(download(e, mk.data(), e->d_mkt.p, mk.size() * sizeof(float)));
-    const float P0S2[2] = {mk[nm - 1], mk[2 * (size_t)nm + nm - 1]};
-    rng->offset += (uint64_t)n;   // the reference leaves d_states after run_zbc_price (src/3:509-510)
+    HW_TRY(wait_results(e));
+    HW_TRY(require_finite(e, res_mom(e, 0), 10));
     out->n_steps_S1 = n;
-    out->price_minus_recal = zbc_price_cv(mom, rng->n_paths, P0S2[0]);
-    out->price_plus_recal = zbc_price_cv(mom + 5, rng->n_paths, P0S2[1]);
-    out->vega_fd_recal = (out->price_plus_recal - out->price_minus_recal) / (2.0f * eps);   // src/3:513
+    recal_result(e, 0, rng->n_paths, eps, out);
     HW_CUDA(e, cudaEventElapsedTime(&out->ms_fd_recal, e->ev0, e->ev1));
     return HW1F_OK;
 }
@@ -1464,78 +1701,39 @@ int hw1f_vega(hw1f_engine* e, hw1f_rng* rng, float S1, float S2, float K, const 
         HW_TRY(hw1f_vega_fd(e, rng, S1, S2, K, P_mkt, f_mkt, eps, n, out));      // normals [n,2n)
         return hw1f_vega_fd_recalibrated(e, rng, S1, S2, K, eps, n, out);        // normals [2n,..)
     }
-    // The three estimators of the reference's main() (src/3:697-834) enqueued back to back -- same launches, same draw
-    // windows and same results as hw1f_vega_pathwise + hw1f_vega_fd + hw1f_vega_fd_recalibrated -- with ONE read-back
-    // at the end instead of a host round trip after each of them.
+    // The three estimators of the reference's main() (src/3:697-834) enqueued back to back -- same draw windows and
+    // same results as hw1f_vega_pathwise + hw1f_vega_fd + hw1f_vega_fd_recalibrated -- seven launches in all (three
+    // jump tables, three simulations, the prices from the parked state); every result lands in mapped pinned host
+    // memory from the kernels' tails, the host waits ONCE.
     HW_CUDA(e, e->d_moments.ensure(4 * (size_t)nm * kMaxRuns));
-    HW_CUDA(e, e->d_out.ensure(4 * (size_t)nm));
     HW_CUDA(e, e->d_mkt.ensure(4 * (size_t)nm));
     double* const res = e->d_moments.p + 4 * (size_t)nm;   // [0,2) pathwise, [8,18) FD, [24,34) recalibrated FD
-    const float sig_m = e->p.sigma - eps, sig_p = e->p.sigma + eps;
-    // the FD arena first: scen_dev() captures the device addresses of the drift tables it names
-    HW_TRY(upload_fd_tables(e, sig_m, sig_p));
-    const ScenDev base = scen_dev(e, e->p.sigma, e->sig_st, 0);
-    ScenDev fd[2] = {scen_dev(e, sig_m, host_sig_st(e->p, sig_m), 2), scen_dev(e, sig_p, host_sig_st(e->p, sig_p), 3)};
-    ScenDev rc[2] = {scen_dev(e, sig_m, host_sig_st(e->p, sig_m), 0), scen_dev(e, sig_p, host_sig_st(e->p, sig_p), 0)};
     HW_TRY(warm_geometry(e, rng));
-    Launch L;
     // pathwise tangent, normals [off, off+n)  (simulate_sensitivity, src/3:251)
     HW_CUDA(e, cudaEventRecord(e->ev0, e->stream));
-    HW_TRY(prepare_launch(e, &rng->seed, 1, rng->first_path, rng->n_paths, rng->offset, &L));
-    HW_TRY(launch_plans_host(e, &base, 1, S1, S2, P_mkt, f_mkt));
-    HW_TRY(launch_pathwise(e, L, base, n, K, res));
-    rng->offset += (uint64_t)n;
+    Finish f0;
+    f0.host_mom = res_mom(e, 0);
+    HW_TRY(pathwise_run(e, rng, S1, S2, K, P_mkt, f_mkt, n, res, f0));
     // CRN finite differences, normals [off+n, off+2n)  (run_finite_difference, src/3:400-446)
     HW_CUDA(e, cudaEventRecord(e->ev1, e->stream));
-    HW_TRY(prepare_launch(e, &rng->seed, 1, rng->first_path, rng->n_paths, rng->offset, &L));
-    HW_TRY(launch_plans_host(e, fd, 2, S1, S2, P_mkt, f_mkt));
-    HW_TRY(launch_zbc(e, L, fd, 2, n, K, res + 8));
-    rng->offset += (uint64_t)n;
+    Finish f1;
+    f1.host_mom = res_mom(e, 1);
+    HW_TRY(fd_run(e, rng, S1, S2, K, P_mkt, f_mkt, eps, n, res + 8, f1));
     // recalibrated finite differences, curves on [off+2n, off+2n+N_STEPS), prices on [off+2n, off+3n)  (src/3:449-525)
     HW_CUDA(e, cudaEventRecord(e->ev2, e->stream));
-    HW_TRY(prepare_launch(e, &rng->seed, 1, rng->first_path, rng->n_paths, rng->offset, &L));
-    const bool one_pass = e->mode == HW1F_MODE_DECOMPOSED && n > 0 && (n % e->stride) == 0 &&
-                          rng->n_paths <= (1ull << 27);
-    HW_TRY(launch_curve(e, L, rc, 2, e->d_moments.p, one_pass ? n : 0));
-    const float inv_dT = 1.0f / e->spacing;
-    for (int s = 0; s < 2; ++s) {
-        float* dP = e->d_mkt.p + 2 * (size_t)s * nm;
-        curve_epilogue_kernel<<<1, ((nm + 31) / 32) * 32, nm * sizeof(float), e->stream>>>(
-            e->d_moments.p + 2 * (size_t)s * nm, nm, rng->n_paths, inv_dT, dP, dP + nm, nullptr);
-        HW_TRY(check_launch(e, "curve_epilogue_kernel"));
-    }
-    HW_TRY(launch_plans(e, rc, 2, S1, S2));
-    if (one_pass) HW_TRY(launch_zbc_from_state(e, L, rc, n, K, res + 24));
-    else HW_TRY(launch_zbc(e, L, rc, 2, n, K, res + 24));
-    rng->offset += (uint64_t)n;
+    HW_TRY(recal_run(e, rng, S1, S2, K, eps, n, res + 24, 2));
     HW_CUDA(e, cudaEventRecord(e->ev3, e->stream));
-    // one read-back: 34 doubles of moments and P(0, T_final) of both recalibrated curves
-    HW_CUDA(e, cudaEventSynchronize(e->ev_stage));
-    HW_TRY(stage_reserve(e, 34 * sizeof(double) + 2 * sizeof(float)));
-    char* hs = static_cast<char*>(e->h_stage);
-    HW_CUDA(e, cudaMemcpyAsync(hs, res, 34 * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
-    for (int s = 0; s < 2; ++s)
-        HW_CUDA(e, cudaMemcpyAsync(hs + 34 * sizeof(double) + s * sizeof(float),
-                                   e->d_mkt.p + 2 * (size_t)s * nm + (nm - 1), sizeof(float), cudaMemcpyDeviceToHost,
-                                   e->stream));
-    HW_CUDA(e, cudaStreamSynchronize(e->stream));
-    double mom[34];
-    float P0S2_rc[2];
-    memcpy(mom, hs, sizeof(mom));
-    memcpy(P0S2_rc, hs + sizeof(mom), sizeof(P0S2_rc));
-    const double np = (double)rng->n_paths;
+    HW_TRY(wait_results(e));
+    HW_TRY(require_finite(e, res_mom(e, 0), 2));
+    HW_TRY(require_finite(e, res_mom(e, 1), 10));
+    HW_TRY(require_finite(e, res_mom(e, 2), 10));
     const float P0S2 = P_mkt[nm - 1];
     out->n_steps_S1 = n;
-    out->vega_pathwise = (float)mom[0] / (float)rng->n_paths;   // sum / N_PATHS in float, src/3:261
-    out->vega_pathwise_f64 = mom[0] / np;
-    const double var = (np > 1) ? (mom[1] - mom[0] * mom[0] / np) / (np - 1.0) : 0.0;
-    out->vega_pathwise_se = (var > 0) ? sqrt(var / np) : 0.0;
-    out->price_minus = zbc_price_cv(mom + 8, rng->n_paths, P0S2);
-    out->price_plus = zbc_price_cv(mom + 13, rng->n_paths, P0S2);
+    pathwise_result(res_mom(e, 0), rng->n_paths, out);
+    out->price_minus = zbc_price_cv(res_mom(e, 1), rng->n_paths, P0S2);
+    out->price_plus = zbc_price_cv(res_mom(e, 1) + 5, rng->n_paths, P0S2);
     out->vega_fd = (out->price_plus - out->price_minus) / (2.0f * eps);                     // src/3:443
-    out->price_minus_recal = zbc_price_cv(mom + 24, rng->n_paths, P0S2_rc[0]);
-    out->price_plus_recal = zbc_price_cv(mom + 29, rng->n_paths, P0S2_rc[1]);
-    out->vega_fd_recal = (out->price_plus_recal - out->price_minus_recal) / (2.0f * eps);   // src/3:513
+    recal_result(e, 2, rng->n_paths, eps, out);
     HW_CUDA(e, cudaEventElapsedTime(&out->ms_pathwise, e->ev0, e->ev1));
     HW_CUDA(e, cudaEventElapsedTime(&out->ms_fd, e->ev1, e->ev2));
     HW_CUDA(e, cudaEventElapsedTime(&out->ms_fd_recal, e->ev2, e->ev3));
@@ -1543,7 +1741,7 @@ int hw1f_vega(hw1f_engine* e, hw1f_rng* rng, float S1, float S2, float K, const 
 }
 
 static int fused_launch(hw1f_engine* e, hw1f_rng* rng, float S1, float S2, float K, const float* P_mkt,
-                        const float* f_mkt, bool fd, float eps, int32_t n_steps_S1, double* d_moments)
+                        const float* f_mkt, bool fd, float eps, int32_t n_steps_S1, double* d_moments, const Finish& fin)
 {
     HW_TRY(require_model(e));
     if (!rng || !P_mkt || !f_mkt || !d_moments) return HW1F_ERR_INVALID;
@@ -1562,11 +1760,10 @@ static int fused_launch(hw1f_engine* e, hw1f_rng* rng, float S1, float S2, float
         sc[1] = scen_dev(e, sig_m, host_sig_st(e->p, sig_m), 2);
         sc[2] = scen_dev(e, sig_p, host_sig_st(e->p, sig_p), 3);
     }
-    // the per-launch jump table first: the plan launches are enqueued while it runs
+    // the bond plans (base, and both bumps) ride on the jump-table launch
+    const PlanJob job = plan_job_host(e, sc, fd ? 3 : 1, S1, S2, P_mkt, f_mkt);
     Launch L;
-    HW_TRY(prepare_launch(e, &rng->seed, 1, rng->first_path, rng->n_paths, rng->offset, &L));
-    HW_TRY(launch_plans_host(e, sc, 1, S1, S2, P_mkt, f_mkt, 0));
-    if (fd) HW_TRY(launch_plans_host(e, sc + 1, 2, S1, S2, P_mkt, f_mkt, 1));
+    HW_TRY(prepare_launch(e, &rng->seed, 1, rng->first_path, rng->n_paths, rng->offset, &L, &job));
     const int nm = e->p.n_mat, next = kFusedExtra + (fd ? kFusedFdExtra : 0), nq = 2 * nm + next;
     HW_CUDA(e, e->d_partials.ensure((size_t)L.grid_x * nq));
     if (e->mode == HW1F_MODE_DECOMPOSED) {
@@ -1576,20 +1773,18 @@ static int fused_launch(hw1f_engine* e, hw1f_rng* rng, float S1, float S2, float
         const FastScen zm = fd ? fast_scen(e, sc[1].sig_st, 2, n) : c0, zp = fd ? fast_scen(e, sc[2].sig_st, 3, n) : c0;
         const FastTangent tg = fast_tangent(e, n);
         const size_t smemf = smem_fast(e, 1);
+        const ModelDev md = model_dev(e);
         if (fd) {
             HW_TRY(set_smem(e, fast_kernel<1, 3, 2>, smemf));
-            fast_kernel<1, 3, 2><<<L.grid_x, kThreads, smemf, e->stream>>>(L.g, L.seeds, model_dev(e), c0, c0, c0, zm, zp, tg,
-                                                                          e->d_plans.p, n, 0, K, e->d_partials.p, nullptr);
+            HW_CUDA(e, launch_k(fast_kernel<1, 3, 2>, dim3(L.grid_x), kThreads, smemf, e->stream, true, L.g, L.seeds, md, c0,
+                                c0, c0, zm, zp, tg, e->d_plans.p, n, 0, K, e->d_partials.p, (float2*)nullptr));
         } else {
             HW_TRY(set_smem(e, fast_kernel<1, 1, 2>, smemf));
-            fast_kernel<1, 1, 2><<<L.grid_x, kThreads, smemf, e->stream>>>(L.g, L.seeds, model_dev(e), c0, c0, c0, c0, c0, tg,
-                                                                          e->d_plans.p, n, 0, K, e->d_partials.p, nullptr);
+            HW_CUDA(e, launch_k(fast_kernel<1, 1, 2>, dim3(L.grid_x), kThreads, smemf, e->stream, true, L.g, L.seeds, md, c0,
+                                c0, c0, c0, c0, tg, e->d_plans.p, n, 0, K, e->d_partials.p, (float2*)nullptr));
         }
         HW_TRY(check_launch(e, "fast_kernel<fused>"));
-        reduce_curve_kernel<<<dim3(nm, 1), 256, 0, e->stream>>>(e->d_partials.p, (int)L.grid_x, nq, 1, nm, c0.emI, c0.emI,
-                                                               2.0f, rng->n_paths, d_moments, nq);
-        HW_TRY(check_launch(e, "reduce_curve_kernel"));
-        HW_TRY(reduce_range(e, 1, L.grid_x, nq, 2 * nm, next, d_moments + 2 * nm, nq));
+        HW_TRY(launch_tail(e, L, L.g.n_paths, nq, 1, c0.emI, c0.emI, 2.0f, d_moments, nq, next, fin));
         rng->offset += (uint64_t)e->p.n_steps;
         return HW1F_OK;
     }
@@ -1605,9 +1800,7 @@ static int fused_launch(hw1f_engine* e, hw1f_rng* rng, float S1, float S2, float
                                                                      e->d_plans.p, n, K, e->d_partials.p);
     }
     HW_TRY(check_launch(e, "fused_kernel"));
-    HW_TRY(reduce_to(e, 1, L.grid_x, nq, d_moments));
-    fused_uncenter_kernel<<<1, ((nm + 31) / 32) * 32, 0, e->stream>>>(d_moments, nm, sc[0].center, rng->n_paths);
-    HW_TRY(check_launch(e, "fused_uncenter_kernel"));
+    HW_TRY(launch_tail(e, L, L.g.n_paths, nq, 1, sc[0].center, sc[0].center, 1.0f, d_moments, nq, next, fin));
     rng->offset += (uint64_t)e->p.n_steps;
     return HW1F_OK;
 }
@@ -1616,7 +1809,9 @@ int hw1f_fused_moments(hw1f_engine* e, hw1f_rng* rng, float S1, float S2, float 
                        const float* f_mkt, int32_t n_steps_S1, double* d_moments)
 {
     if (!e) return HW1F_ERR_INVALID;
-    return fused_launch(e, rng, S1, S2, K, P_mkt, f_mkt, false, 0.0f, n_steps_S1, d_moments);
+    Finish fin;
+    fin.exchange = true;
+    return fused_launch(e, rng, S1, S2, K, P_mkt, f_mkt, false, 0.0f, n_steps_S1, d_moments, fin);
 }
 
 int hw1f_fused_fd_moments(hw1f_engine* e, hw1f_rng* rng, float S1, float S2, float K, const float* P_mkt,
@@ -1624,38 +1819,21 @@ int hw1f_fused_fd_moments(hw1f_engine* e, hw1f_rng* rng, float S1, float S2, flo
 {
     if (!e) return HW1F_ERR_INVALID;
     HW_REQUIRE(e, eps > 0.0f && eps < e->p.sigma, "eps must be in (0, sigma)");
-    return fused_launch(e, rng, S1, S2, K, P_mkt, f_mkt, true, eps, n_steps_S1, d_moments);
+    Finish fin;
+    fin.exchange = true;
+    return fused_launch(e, rng, S1, S2, K, P_mkt, f_mkt, true, eps, n_steps_S1, d_moments, fin);
 }
 
-int hw1f_fused_finish(hw1f_engine* e, const double* d_moments, uint64_t n_paths_total, float P0S2, float eps,
-                      int32_t n_steps_S1, float* P, float* f, float* P_se, hw1f_zbc_result* zbc, hw1f_vega_result* vega)
+// finalisation of a fused moment vector that sits in the result area (moments from index 2*n_mat on, curves)
+static int fused_results(hw1f_engine* e, int area, uint64_t n_paths_total, float P0S2, float eps, int32_t n_steps_S1,
+                         float* P, float* f, float* P_se, hw1f_zbc_result* zbc, hw1f_vega_result* vega)
 {
-    HW_TRY(require_model(e));
-    if (!d_moments || !P || !f || !zbc || !vega) return HW1F_ERR_INVALID;
-    HW_CUDA(e, cudaSetDevice(e->device));
-    HW_REQUIRE(e, n_paths_total >= 1 && n_paths_total < (1ull << 40), "n_paths_total outside [1, 2^40)");
     const bool fd = eps > 0.0f;
     const int nm = e->p.n_mat, next = kFusedExtra + (fd ? kFusedFdExtra : 0);
-    // curve epilogue on the device, then ONE read-back of (P, f, P_se) and the S1 block of the moment vector
-    HW_CUDA(e, e->d_out.ensure(4 * (size_t)nm));
-    float* dP = e->d_out.p;
-    curve_epilogue_kernel<<<1, ((nm + 31) / 32) * 32, nm * sizeof(float), e->stream>>>(
-        d_moments, nm, n_paths_total, 1.0f / e->spacing, dP, dP + nm, dP + 2 * nm);
-    HW_TRY(check_launch(e, "curve_epilogue_kernel"));
-    const size_t bytes_ext = (size_t)next * sizeof(double), bytes_cur = 3 * (size_t)nm * sizeof(float);
-    HW_CUDA(e, cudaEventSynchronize(e->ev_stage));
-    HW_TRY(stage_reserve(e, bytes_ext + bytes_cur));
-    char* hs = static_cast<char*>(e->h_stage);
-    HW_CUDA(e, cudaMemcpyAsync(hs, d_moments + 2 * nm, bytes_ext, cudaMemcpyDeviceToHost, e->stream));
-    HW_CUDA(e, cudaMemcpyAsync(hs + bytes_ext, dP, bytes_cur, cudaMemcpyDeviceToHost, e->stream));
-    HW_CUDA(e, cudaStreamSynchronize(e->stream));
-    std::vector<double> ext(next);
-    memcpy(ext.data(), hs, bytes_ext);
-    HW_TRY(require_finite(e, ext.data(), next));
-    memcpy(P, hs + bytes_ext, nm * sizeof(float));
-    memcpy(f, hs + bytes_ext + nm * sizeof(float), nm * sizeof(float));
-    if (P_se) memcpy(P_se, hs + bytes_ext + 2 * nm * sizeof(float), nm * sizeof(float));
-    zbc_algebra(ext.data(), n_paths_total, P0S2, n_steps_S1, zbc);
+    const double* ext = res_mom(e, area) + 2 * (size_t)nm;
+    HW_TRY(require_finite(e, ext, next));
+    HW_TRY(read_curve(e, area, 0, P, f, P_se));
+    zbc_algebra(ext, n_paths_total, P0S2, n_steps_S1, zbc);
     memset(vega, 0, sizeof(*vega));
     vega->n_steps_S1 = n_steps_S1;
     const double np2 = 2.0 * (double)n_paths_total, np1 = (double)n_paths_total;
@@ -1665,11 +1843,30 @@ int hw1f_fused_finish(hw1f_engine* e, const double* d_moments, uint64_t n_paths_
     const double var_pair = (np1 > 1) ? (ext[6] - np1 * mean_pair * mean_pair) / (np1 - 1.0) : 0.0;
     vega->vega_pathwise_se = (var_pair > 0) ? 0.5 * sqrt(var_pair / np1) : 0.0;
     if (fd) {
-        vega->price_minus = zbc_price_cv(ext.data() + kFusedExtra, n_paths_total, P0S2);
-        vega->price_plus = zbc_price_cv(ext.data() + kFusedExtra + 5, n_paths_total, P0S2);
+        vega->price_minus = zbc_price_cv(ext + kFusedExtra, n_paths_total, P0S2);
+        vega->price_plus = zbc_price_cv(ext + kFusedExtra + 5, n_paths_total, P0S2);
         vega->vega_fd = (vega->price_plus - vega->price_minus) / (2.0f * eps);
     }
     return HW1F_OK;
+}
+
+int hw1f_fused_finish(hw1f_engine* e, const double* d_moments, uint64_t n_paths_total, float P0S2, float eps,
+                      int32_t n_steps_S1, float* P, float* f, float* P_se, hw1f_zbc_result* zbc, hw1f_vega_result* vega)
+{
+    HW_TRY(require_model(e));
+    if (!d_moments || !P || !f || !zbc || !vega) return HW1F_ERR_INVALID;
+    HW_CUDA(e, cudaSetDevice(e->device));
+    HW_REQUIRE(e, n_paths_total >= 1 && n_paths_total < (1ull << 40), "n_paths_total outside [1, 2^40)");
+    const int nm = e->p.n_mat, next = kFusedExtra + (eps > 0.0f ? kFusedFdExtra : 0);
+    // curve epilogue on the device and the whole vector into the result area: one launch, one wait
+    Finish fin;
+    fin.host_mom = res_mom(e, 0);
+    fin.epi = true;
+    fin.n_total = n_paths_total;
+    fin.host_curve = res_curve(e, 0);
+    HW_TRY(publish(e, 1, 1, const_cast<double*>(d_moments), 2 * nm + next, next, fin));
+    HW_TRY(wait_results(e));
+    return fused_results(e, 0, n_paths_total, P0S2, eps, n_steps_S1, P, f, P_se, zbc, vega);
 }
 
 int hw1f_fused(hw1f_engine* e, hw1f_rng* rng, float S1, float S2, float K, const float* P_mkt, const float* f_mkt,
@@ -1685,10 +1882,16 @@ int hw1f_fused(hw1f_engine* e, hw1f_rng* rng, float S1, float S2, float K, const
     const int nm = e->p.n_mat;
     HW_CUDA(e, e->d_moments.ensure(4 * (size_t)nm * kMaxRuns));
     HW_TRY(warm_geometry(e, rng));
+    Finish fin;
+    fin.host_mom = res_mom(e, 0);
+    fin.epi = true;
+    fin.n_total = rng->n_paths;
+    fin.host_curve = res_curve(e, 0);
     HW_CUDA(e, cudaEventRecord(e->ev0, e->stream));
-    HW_TRY(fused_launch(e, rng, S1, S2, K, P_mkt, f_mkt, true, eps, n, e->d_moments.p));
+    HW_TRY(fused_launch(e, rng, S1, S2, K, P_mkt, f_mkt, true, eps, n, e->d_moments.p, fin));
     HW_CUDA(e, cudaEventRecord(e->ev1, e->stream));
-    HW_TRY(hw1f_fused_finish(e, e->d_moments.p, rng->n_paths, P_mkt[nm - 1], eps, n, P, f, P_se, zbc, vega));
+    HW_TRY(wait_results(e));
+    HW_TRY(fused_results(e, 0, rng->n_paths, P_mkt[nm - 1], eps, n, P, f, P_se, zbc, vega));
     float ms = 0.f;
     HW_CUDA(e, cudaEventElapsedTime(&ms, e->ev0, e->ev1));
     vega->ms_pathwise = vega->ms_fd = ms;
@@ -1773,7 +1976,7 @@ int hw1f_reduction_bench(hw1f_engine* e, hw1f_rng* rng, int32_t method, float S1
     int32_t n = 0;
     HW_TRY(resolve_steps(e, S1, n_steps_S1, &n));
     const ScenDev sc = scen_dev(e, e->p.sigma, e->sig_st, 0);
-    HW_TRY(launch_plans_host(e, &sc, 1, S1, S2, P_mkt, f_mkt));
+    HW_TRY(launch_plan_job(e, plan_job_host(e, &sc, 1, S1, S2, P_mkt, f_mkt)));
     HW_CUDA(e, e->d_moments.ensure(4 * (size_t)e->p.n_mat * kMaxRuns));
     HW_CUDA(e, e->d_out.ensure(64));
     float* d_sum = e->d_out.p;
@@ -1872,6 +2075,23 @@ int hw1f_pipe_probe(hw1f_engine* e, int32_t which, int32_t iters, float* ms, dou
     const double per_thread = (which == 6) ? (double)iters * kProbeUnroll * 29.0
                                            : (double)iters * kProbeUnroll * kProbeChains;
     *thread_instr = per_thread * (double)blocks * threads;
+    return HW1F_OK;
+}
+
+// engine side of hw1f_comm_attach (hw1f_comm.cu); not part of the public header
+int hw1f_engine_attach_comm_internal(hw1f_engine* e, const void* comm_dev, unsigned* epoch, int on)
+{
+    if (!e || (on && (!comm_dev || !epoch))) return HW1F_ERR_INVALID;
+    HW_CUDA(e, cudaSetDevice(e->device));
+    HW_CUDA(e, cudaStreamSynchronize(e->stream));
+    e->comm_on = on != 0;
+    if (on) {
+        e->comm = *static_cast<const CommDev*>(comm_dev);
+        e->comm_epoch = epoch;
+    } else {
+        e->comm = CommDev{};
+        e->comm_epoch = nullptr;
+    }
     return HW1F_OK;
 }
 

@@ -22,67 +22,21 @@
 #include <string>
 
 #include "../../include/hw1f.h"
+#include "hw1f_comm.cuh"
+
+using namespace hw1f;
+
+// the engine side of hw1f_comm_attach (hw1f_api.cu): hands the mapped mailboxes and the epoch counter to the
+// engine, whose *_moments entry points then all-reduce in the tail of their simulation kernel
+extern "C" int hw1f_engine_attach_comm_internal(hw1f_engine* e, const void* comm_dev, unsigned* epoch, int on);
 
 namespace {
 
-constexpr int kMaxWorld = 8;
-constexpr int kMaxCount = 256;
-constexpr unsigned kSpinLimit = 20000000u;  // a few seconds of polling: far beyond any healthy skew, still finite
-
-struct Mailbox {
-    double slots[2][kMaxWorld][kMaxCount];
-    unsigned flags[2][kMaxWorld];
-    unsigned timeouts;
-};
-
-struct CommDev {
-    Mailbox* peer[kMaxWorld];
-    int rank, world;
-};
-
-// system-scope release / acquire on the mailbox flags (the payload stores above the release are plain stores)
-__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v)
-{
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p)
-{
-    unsigned v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-
-__global__ void __launch_bounds__(kMaxCount)
+// the exchange as a launch of its own (hw1f_comm_allreduce): one block, device code shared with the kernel tails
+__global__ void __launch_bounds__(256)
 peer_allreduce_kernel(CommDev c, double* __restrict__ data, int count, unsigned epoch)
 {
-    __shared__ int s_timed_out;
-    const int i = threadIdx.x;
-    const int p = epoch & 1u;
-    if (i == 0) s_timed_out = 0;
-    const double mine = (i < count) ? data[i] : 0.0;
-    // 1. post into every mailbox (including our own)
-    if (i < count)
-        for (int r = 0; r < c.world; ++r) c.peer[r]->slots[p][c.rank][i] = mine;
-    __threadfence_system();   // every thread's payload stores are ordered before the block-wide barrier ...
-    __syncthreads();
-    if (i < c.world) st_release_sys(&c.peer[i]->flags[p][c.rank], epoch);   // ... and published by the release
-    // 2. wait for every peer's post of this epoch in OUR mailbox
-    Mailbox* me = c.peer[c.rank];
-    if (i < c.world) {
-        unsigned spins = 0;
-        while (ld_acquire_sys(&me->flags[p][i]) != epoch) {
-            if (++spins > kSpinLimit) { atomicAdd(&me->timeouts, 1u); s_timed_out = 1; break; }
-            __nanosleep(128);
-        }
-    }
-    __syncthreads();
-    // 3. rank-ordered sum; a lost peer poisons the result instead of letting stale slots through: every
-    // *_finish call rejects a non-finite moment vector (HW1F_ERR_COMM)
-    if (i < count) {
-        double acc = 0.0;
-        for (int r = 0; r < c.world; ++r) acc += *(volatile double*)&me->slots[p][r][i];
-        data[i] = s_timed_out ? __longlong_as_double(0x7ff8000000000000ll) : acc;
-    }
+    block_peer_allreduce(c, data, count, epoch);
 }
 
 }  // namespace
@@ -92,7 +46,8 @@ struct hw1f_comm {
     int device = 0, rank = -1, world = 0;
     Mailbox* local = nullptr;
     CommDev dev{};
-    bool opened[kMaxWorld] = {false};
+    bool opened[kCommMaxWorld] = {false};
+    bool attached = false;
     unsigned epoch = 0;
     cudaStream_t stream = nullptr;
     std::string err;
@@ -104,7 +59,7 @@ const char* hw1f_comm_last_error(const hw1f_comm* c) { return c ? c->err.c_str()
 
 int hw1f_comm_create(hw1f_engine* eng, int world, void* ipc_handle64, hw1f_comm** out)
 {
-    if (!eng || !ipc_handle64 || !out || world < 1 || world > kMaxWorld) return HW1F_ERR_INVALID;
+    if (!eng || !ipc_handle64 || !out || world < 1 || world > kCommMaxWorld) return HW1F_ERR_INVALID;
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
     hw1f_comm* c = new (std::nothrow) hw1f_comm();
     if (!c) return HW1F_ERR_INVALID;
@@ -155,13 +110,21 @@ int hw1f_comm_connect(hw1f_comm* c, int rank, const void* all_handles, void* cud
 int hw1f_comm_allreduce(hw1f_comm* c, double* d_data, int32_t count)
 {
     if (!c || !d_data || c->rank < 0) return HW1F_ERR_INVALID;
-    if (count < 1 || count > kMaxCount) { c->err = "count must be in [1,256]"; return HW1F_ERR_INVALID; }
+    if (count < 1 || count > kCommMaxCount) { c->err = "count must be in [1,512]"; return HW1F_ERR_INVALID; }
     cudaSetDevice(c->device);
-    ++c->epoch;
-    peer_allreduce_kernel<<<1, kMaxCount, 0, c->stream>>>(c->dev, d_data, count, c->epoch);
+    ++c->epoch;   // shared with the engine's kernel tails when attached: one sequence of epochs per communicator
+    peer_allreduce_kernel<<<1, 256, 0, c->stream>>>(c->dev, d_data, count, c->epoch);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { c->err = std::string("peer_allreduce_kernel: ") + cudaGetErrorString(e); return HW1F_ERR_CUDA; }
     return HW1F_OK;
+}
+
+int hw1f_comm_attach(hw1f_comm* c, int on)
+{
+    if (!c || c->rank < 0) return HW1F_ERR_INVALID;
+    const int st = hw1f_engine_attach_comm_internal(c->eng, &c->dev, &c->epoch, on);
+    if (st == HW1F_OK) c->attached = on != 0;
+    return st;
 }
 
 int hw1f_comm_timeouts(hw1f_comm* c, uint32_t* n)
@@ -177,6 +140,7 @@ int hw1f_comm_destroy(hw1f_comm* c)
 {
     if (!c) return HW1F_OK;
     cudaSetDevice(c->device);
+    if (c->attached) hw1f_engine_attach_comm_internal(c->eng, &c->dev, &c->epoch, 0);
     cudaDeviceSynchronize();
     for (int r = 0; r < c->world; ++r)
         if (c->opened[r]) cudaIpcCloseMemHandle(c->dev.peer[r]);

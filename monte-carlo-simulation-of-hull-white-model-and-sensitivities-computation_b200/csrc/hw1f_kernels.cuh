@@ -77,32 +77,6 @@ struct BondPlan {
 // =================================================================================================
 // per-launch preparation
 // =================================================================================================
-// U[run][w][lo] = word w of J^lo * v0'(run), lo < L.  One warp per (run, lo).
-__global__ void __launch_bounds__(256)
-prep_lo_kernel(SeedArgs seeds, int n_runs, uint32_t L_log2, const uint32_t* __restrict__ Jpow2,
-               uint32_t* __restrict__ U)
-{
-    const int lane = threadIdx.x & 31;
-    const uint32_t L = 1u << L_log2;
-    const unsigned long long wid = (unsigned long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (wid >= (unsigned long long)n_runs * L) return;
-    const int run = (int)(wid >> L_log2);
-    const uint32_t lo = (uint32_t)(wid & (L - 1));
-    uint32_t v[5];
-#pragma unroll
-    for (int w = 0; w < 5; ++w) v[w] = seeds.s[run].v0[w];
-    for (uint32_t k = 0; k < L_log2; ++k)
-        if ((lo >> k) & 1u) warp_matvec(Jpow2 + (size_t)k * 800, v, lane);
-    if (lane < 5) {
-        uint32_t out = v[0];
-        if (lane == 1) out = v[1];
-        if (lane == 2) out = v[2];
-        if (lane == 3) out = v[3];
-        if (lane == 4) out = v[4];
-        U[((size_t)run * 5 + lane) * L + lo] = out;
-    }
-}
-
 // interpolate() of common.cuh:187-196 as compiled: T/spacing -> T*10, alpha via one FFMA.  d0 = data[idx],
 // d1 = data[idx+1]; idx >= n_mat-1 returns d0 (= data[n_mat-1])
 __device__ __forceinline__ float interp_pts(float d0, float d1, int idx, float T, const ModelDev& md)
@@ -126,19 +100,14 @@ struct MktPts {
     int idx_S2, idx_S1;
 };
 
-__global__ void bond_plan_kernel(ModelDev md, ScenDev sc0, ScenDev sc1, int n_scen, float S1, float S2,
-                                 const float* __restrict__ P_mkt0, const float* __restrict__ f_mkt0,
-                                 const float* __restrict__ P_mkt1, const float* __restrict__ f_mkt1,
-                                 BondPlan* __restrict__ plans, MktPts pts, int use_pts)
+// one bond plan (common.cuh:180-225, src/3:15-19) in the reference's MUFU sequence.  use_pts: the six market values
+// were picked on the host (every scenario prices on the same curves); else device-resident curves
+__device__ __forceinline__ BondPlan compute_plan(const ModelDev& md, float sigma, float sig_st, float S1, float S2,
+                                                 const float* __restrict__ P_mkt, const float* __restrict__ f_mkt,
+                                                 const MktPts& pts, int use_pts)
 {
-    const int s = threadIdx.x;
-    if (s >= n_scen) return;
-    const ScenDev sc = s ? sc1 : sc0;
-    const float* P_mkt = s ? P_mkt1 : P_mkt0;
-    const float* f_mkt = s ? f_mkt1 : f_mkt0;
-    const float a = md.a, sigma = sc.sigma;
+    const float a = md.a;
     const float B = mul_(sub_(1.0f, mufu_ex2(mul_(mul_(sub_(S2, S1), a), -kLog2e))), mufu_rcp(a));
-    // use_pts: host-resident market curves (every scenario prices on the same curves); else device curves
     const float P0T = use_pts ? interp_pts(pts.P_S2[0], pts.P_S2[1], pts.idx_S2, S2, md) : interp_mkt(P_mkt, S2, md);
     const float P0t = use_pts ? interp_pts(pts.P_S1[0], pts.P_S1[1], pts.idx_S1, S1, md) : interp_mkt(P_mkt, S1, md);
     const float f0t = use_pts ? interp_pts(pts.f_S1[0], pts.f_S1[1], pts.idx_S1, S1, md) : interp_mkt(f_mkt, S1, md);
@@ -154,8 +123,66 @@ __global__ void bond_plan_kernel(ModelDev md, ScenDev sc0, ScenDev sc1, int n_sc
     p.A = mul_(ratio, E);
     p.om2 = om2;
     p.xk = mul_(om2, mul_(mufu_rcp(add_(a, a)), sigma));   // sigma/(2a) (1-e^{-2aS1}), src/3:17-18
-    p.c_t = mul_(mufu_rcp(sigma), sc.sig_st);               // d_sig_st / d_sigma,       src/3:60
-    plans[s] = p;
+    p.c_t = mul_(mufu_rcp(sigma), sig_st);                  // d_sig_st / d_sigma,       src/3:60
+    return p;
+}
+
+// up to three bond plans computed as a side job of another launch (prep_lo_kernel's extra block, or the tail of a
+// curve kernel for the recalibrated curves): no launch of its own
+struct PlanJob {
+    int n_scen;                    // 0: no job
+    float sigma[3], sig_st[3];
+    float S1, S2;
+    MktPts pts;                    // use_pts = 1: host-picked market values
+    int use_pts;
+    const float* P_mkt[2];         // use_pts = 0: device curves of scenario 0 / 1
+    const float* f_mkt[2];
+    BondPlan* plans;               // output, n_scen entries
+};
+
+__device__ __forceinline__ void run_plan_job(const ModelDev& md, const PlanJob& job, int s)
+{
+    if (s >= job.n_scen) return;
+    const int c = (s < 2) ? s : 1;
+    job.plans[s] = compute_plan(md, job.sigma[s], job.sig_st[s], job.S1, job.S2, job.P_mkt[c], job.f_mkt[c], job.pts,
+                                job.use_pts);
+}
+
+// a plan job as a launch of its own (batched entry points price many launches on one set of plans)
+__global__ void plan_job_kernel(ModelDev md, PlanJob job) { run_plan_job(md, job, threadIdx.x); }
+
+// U[run][w][lo] = word w of J^lo * v0'(run), lo < L.  One warp per (run, lo); one extra block (the last) runs the
+// launch's plan job.  The dependent simulation kernel is launched with programmatic stream serialisation: this kernel
+// releases it at once (its prologue overlaps the table build) and the dependent waits with griddepcontrol.wait
+// before it touches U or the plans.
+__global__ void __launch_bounds__(256)
+prep_lo_kernel(SeedArgs seeds, int n_runs, uint32_t L_log2, const uint32_t* __restrict__ Jpow2,
+               uint32_t* __restrict__ U, ModelDev md, PlanJob job)
+{
+    asm volatile("griddepcontrol.launch_dependents;");
+    const int lane = threadIdx.x & 31;
+    const uint32_t L = 1u << L_log2;
+    if (blockIdx.x == gridDim.x - 1) {          // plan block
+        run_plan_job(md, job, threadIdx.x);
+        return;
+    }
+    const unsigned long long wid = (unsigned long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (wid >= (unsigned long long)n_runs * L) return;
+    const int run = (int)(wid >> L_log2);
+    const uint32_t lo = (uint32_t)(wid & (L - 1));
+    uint32_t v[5];
+#pragma unroll
+    for (int w = 0; w < 5; ++w) v[w] = seeds.s[run].v0[w];
+    for (uint32_t k = 0; k < L_log2; ++k)
+        if ((lo >> k) & 1u) warp_matvec(Jpow2 + (size_t)k * 800, v, lane);
+    if (lane < 5) {
+        uint32_t out = v[0];
+        if (lane == 1) out = v[1];
+        if (lane == 2) out = v[2];
+        if (lane == 3) out = v[3];
+        if (lane == 4) out = v[4];
+        U[((size_t)run * 5 + lane) * L + lo] = out;
+    }
 }
 
 // W[h] = window table of J^((hi_base+h) * 2^L_log2).  One block of 160 threads per h.
@@ -663,16 +690,16 @@ reduce_curve_kernel(const double* __restrict__ partials, int n_blocks, int strid
 // epilogues (path-independent; device-side so that rcp/lg2/ex2 are the same MUFU results the
 // reference's epilogue kernels produce)
 // =================================================================================================
-// compute_average_and_forward (market_data.cuh:101-127) + standard error of P
-__global__ void curve_epilogue_kernel(const double* __restrict__ moments, int n_mat, unsigned long long n_pairs,
-                                      float inv_dT, float* __restrict__ P, float* __restrict__ f,
-                                      float* __restrict__ P_se)
+// compute_average_and_forward (market_data.cuh:101-127) + standard error of P, executed by ONE block (any size);
+// s_P: n_mat floats of shared scratch.  P_se may be null.  Used by curve_epilogue_kernel and by the tail of the
+// simulation kernels (hw1f_tail.cuh).
+__device__ __forceinline__ void curve_epilogue_block(const double* __restrict__ moments, int n_mat, unsigned long long n_pairs,
+                                                     float inv_dT, float* __restrict__ P, float* __restrict__ f,
+                                                     float* __restrict__ P_se, float* s_P)
 {
-    extern __shared__ float s_P[];
-    const int m = threadIdx.x;
     // (float)n_paths of the reference (an int there); same value from the 64-bit count, and defined beyond 2^31
     const float n_paths_f = __ull2float_rn(2ull * n_pairs);
-    if (m < n_mat) {
+    for (int m = threadIdx.x; m < n_mat; m += blockDim.x) {
         // P_sum[0] = 2.0f * N_PATHS (market_data.cuh:76-78)
         const float sum = (m == 0) ? mul_(2.0f, __ull2float_rn(n_pairs)) : __double2float_rn(moments[m]);
         const float avg = mul_(sum, mufu_rcp(n_paths_f));
@@ -692,7 +719,7 @@ __global__ void curve_epilogue_kernel(const double* __restrict__ moments, int n_
         }
     }
     __syncthreads();
-    if (m < n_mat) {
+    for (int m = threadIdx.x; m < n_mat; m += blockDim.x) {
         const int first = (m == 0) ? 0 : m - 1;
         const int last = (m == n_mat - 1) ? n_mat - 1 : m + 1;
         const float nscale = ((m == 0) || (m == n_mat - 1)) ? -1.0f : -0.5f;
@@ -701,6 +728,15 @@ __global__ void curve_epilogue_kernel(const double* __restrict__ moments, int n_
         const float dl = fma_(mufu_lg2(s_P[last]), kLn2, -lf);
         f[m] = mul_(c, dl);
     }
+    __syncthreads();
+}
+
+__global__ void curve_epilogue_kernel(const double* __restrict__ moments, int n_mat, unsigned long long n_pairs,
+                                      float inv_dT, float* __restrict__ P, float* __restrict__ f,
+                                      float* __restrict__ P_se)
+{
+    extern __shared__ float s_P[];
+    curve_epilogue_block(moments, n_mat, n_pairs, inv_dT, P, f, P_se, s_P);
 }
 
 // recover_theta (src/2_option_pricing.cu:14-35) + compute_derivative (common.cuh:250-258)

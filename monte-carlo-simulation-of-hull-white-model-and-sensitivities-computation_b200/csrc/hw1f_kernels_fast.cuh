@@ -99,6 +99,9 @@ fast_kernel(StreamGeom g, SeedArgs seeds, ModelDev md, FastScen cs0, FastScen cs
             double* __restrict__ partials, float2* __restrict__ dump)
 {
     extern __shared__ __align__(16) uint32_t smem[];
+    // the tail kernel behind this launch (hw1f_tail.cuh) may be made resident as soon as every block of this grid has
+    // started: it parks in griddepcontrol.wait until the grid has completed and flushed
+    asm volatile("griddepcontrol.launch_dependents;");
     constexpr int kS1 = NZBC * 5 + (PW ? 3 : 0);
     const int n_mat = md.n_mat;
     const int nqc = NCUR * 2 * n_mat;
@@ -132,6 +135,10 @@ fast_kernel(StreamGeom g, SeedArgs seeds, ModelDev md, FastScen cs0, FastScen cs
     // per-scenario exponents: exp(-/+ c q) = ex2(-/+ q * (c log2e))
     const float kc0 = mul_(cs0.c, kLog2e), kc1 = mul_(cs1.c, kLog2e);
     const float zA0 = mul_(cs0.c, md.qA), zB0 = -mul_(cs0.c, md.qB), zA1 = mul_(cs1.c, md.qA), zB1 = -mul_(cs1.c, md.qB);
+
+    // launched with programmatic stream serialisation behind prep_lo_kernel: everything above overlapped it; the
+    // per-launch table U and the bond plans are read only below this point
+    asm volatile("griddepcontrol.wait;" ::: "memory");
 
     for (unsigned long long chunk = blockIdx.x; chunk < g.n_chunks; chunk += gridDim.x) {
         ThreadStreams t = derive_streams(g, seeds, run, chunk, win);

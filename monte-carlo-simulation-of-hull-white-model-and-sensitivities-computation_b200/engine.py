@@ -177,14 +177,15 @@ class Engine:
         return n.value
 
     # -- Q1: simulate_zcb + compute_average_and_forward (src/1_bond_pricing.cu:65-79) --
-    def bond_curve(self, rng, with_se=True):
+    def bond_curve(self, rng, with_se=True, timing=True):
+        """timing=False: no CUDA events around the simulation (sim_ms is None)"""
         P = np.zeros(self.n_mat, np.float32)
         f = np.zeros(self.n_mat, np.float32)
         se = np.zeros(self.n_mat, np.float32) if with_se else None
         ms = C.c_float()
         self._check(self._lib.hw1f_bond_curve(self._h, rng._h, _ptr(P), _ptr(f), _ptr(se) if with_se else None,
-                                              C.byref(ms)))
-        return {"P": P, "f": f, "P_se": se, "sim_ms": ms.value}
+                                              C.byref(ms) if timing else None))
+        return {"P": P, "f": f, "P_se": se, "sim_ms": ms.value if timing else None}
 
     def bond_curve_moments(self, rng, d_moments_ptr):
         """async: device pointer to 2*n_mat doubles (e.g. a torch.float64 CUDA tensor's data_ptr())."""

@@ -74,16 +74,27 @@ class PeerAllReduce:
             self._lib.hw1f_comm_destroy(self._h)
             self._h = None
             raise RuntimeError("hw1f_comm_connect: " + msg)
+        self.attached = False
         dist.barrier()
 
     def all_reduce(self, moments):
-        """in-place rank-ordered SUM of a float64 CUDA tensor with <= 256 elements (async, stream ordered)"""
-        if moments.dtype != torch.float64 or moments.numel() > 256:
-            raise TypeError("float64 tensor with at most 256 elements")
+        """in-place rank-ordered SUM of a float64 CUDA tensor with <= 512 elements (async, stream ordered)"""
+        if moments.dtype != torch.float64 or moments.numel() > 512:
+            raise TypeError("float64 tensor with at most 512 elements")
         st = self._lib.hw1f_comm_allreduce(self._h, self._C.c_void_p(moments.data_ptr()), moments.numel())
         if st != 0:
             raise RuntimeError(self._lib.hw1f_comm_last_error(self._h).decode())
         return moments
+
+    def attach(self, on=True):
+        """on: every engine.*_moments call from now on returns the ALL-REDUCED vector -- the last block of the
+        simulation kernel's reduction posts it to the peers itself (no separate collective launch).  Every rank
+        must make the same calls in the same order."""
+        st = self._lib.hw1f_comm_attach(self._h, 1 if on else 0)
+        if st != 0:
+            raise RuntimeError(f"hw1f_comm_attach failed with status {st}")
+        self.attached = bool(on)
+        return self
 
     def timeouts(self):
         n = self._C.c_uint32()
