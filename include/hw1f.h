@@ -93,6 +93,11 @@ int hw1f_default_params(hw1f_params* out);
 /* compute_constants() + compute_drift_tables(): every cudaMemcpyToSymbol of
  * common.cuh:82-83,98-106 and src/3:416-420,428-432,439-441,453-455,518-520. */
 int hw1f_set_model(hw1f_engine* eng, const hw1f_params* p);
+/* Configuration space: n_steps must be a multiple of n_mat - 1 (the reference's #error, common.cuh:25-27).  The curve
+ * entry points (hw1f_bond_curve*, hw1f_fused*, hw1f_vega_fd_recalibrated, the recalibration leg of hw1f_vega) walk a
+ * whole Box-Muller pair (two steps) at a time and need an EVEN save stride n_steps / (n_mat - 1) and an even normal
+ * offset; for an odd stride (e.g. n_steps = 500, n_mat = 101) they return HW1F_ERR_UNSUPPORTED with a message, while
+ * hw1f_zbc_cv*, hw1f_vega_pathwise*, hw1f_vega_fd and hw1f_sample_paths take any step count and offset parity. */
 int hw1f_get_model(const hw1f_engine* eng, hw1f_params* out);
 /* host copies of the derived constants, for callers that print them */
 typedef struct hw1f_constants {
@@ -136,6 +141,13 @@ int hw1f_bond_curve(hw1f_engine* eng, hw1f_rng* rng, float* P, float* f, float* 
 int hw1f_bond_curve_moments(hw1f_engine* eng, hw1f_rng* rng, double* d_moments);
 int hw1f_bond_curve_finish(hw1f_engine* eng, const double* d_moments, uint64_t n_paths_total,
                            float* P, float* f, float* P_se);
+/* Standard errors of f(0,T) and theta(T) for the LAST bond-curve launch on this engine (hw1f_bond_curve or
+ * hw1f_bond_curve_moments; its per-block partial sums are still resident): covariance of P at neighbouring maturities
+ * by batch means over the simulation blocks (independent batches of 1024 subsequences), then the delta method through
+ * compute_average_and_forward (market_data.cuh:101-127) and recover_theta (src/2:14-35).  The reference reports no
+ * interval for either; SURVEY 7.3-4 makes "inside the 95 % CI" the parity criterion for them.  Any output may be NULL;
+ * P_se_batch is the batch-means standard error of P (cross-check of the exact P_se).  Needs >= 8 blocks. */
+int hw1f_bond_curve_ci(hw1f_engine* eng, float* f_se, float* theta_se, float* P_se_batch);
 
 /* ---- Q2a: theta calibration --------------------------------------------------------- */
 /* recover_theta<<<1,N_MAT>>> (src/2_option_pricing.cu:14-35,82). All arrays [n_mat]. */
@@ -156,6 +168,10 @@ typedef struct hw1f_zbc_result {
     float corr;             /* rho of src/2:281                                        */
     /* additions (double algebra on the double moments) */
     double price_cv_f64, beta_f64, se_raw, se_cv, ci95_lo, ci95_hi;
+    /* standard errors of beta* and rho from the five moments (the reference reports neither): regression slope,
+     * sqrt((1 - rho^2) var_X / (var_Y (n - 2))), and Fisher's (1 - rho^2) / sqrt(n - 3), with ONE degree of freedom per
+     * antithetic pair (the twins are dependent): n = n_total / 2 */
+    double beta_se, corr_f64, corr_se;
 } hw1f_zbc_result;
 
 /* simulate_ZBC_control_variate<<<NB,NTPB>>> + host algebra (common.cuh:286-409; src/2:136,246;

@@ -35,6 +35,7 @@ class ZbcResult(C.Structure):
         ("price_raw", C.c_float), ("price_cv", C.c_float), ("corr_single", C.c_float), ("corr", C.c_float),
         ("price_cv_f64", C.c_double), ("beta_f64", C.c_double), ("se_raw", C.c_double), ("se_cv", C.c_double),
         ("ci95_lo", C.c_double), ("ci95_hi", C.c_double),
+        ("beta_se", C.c_double), ("corr_f64", C.c_double), ("corr_se", C.c_double),
     ]
 
     def as_dict(self):
@@ -85,6 +86,7 @@ SYMBOLS = {
     "hw1f_bond_curve": (C.c_int, [_P, _P, _P, _P, _P, _F]),
     "hw1f_bond_curve_moments": (C.c_int, [_P, _P, _P]),
     "hw1f_bond_curve_finish": (C.c_int, [_P, _P, C.c_uint64, _P, _P, _P]),
+    "hw1f_bond_curve_ci": (C.c_int, [_P, _P, _P, _P]),
     "hw1f_theta_calibrate": (C.c_int, [_P, _P, _P, _P, _P]),
     "hw1f_zbc_cv": (C.c_int, [_P, _P, C.c_float, C.c_float, C.c_float, _P, _P, C.c_int32, C.POINTER(ZbcResult), _F]),
     "hw1f_zbc_cv_moments": (C.c_int, [_P, _P, C.c_float, C.c_float, C.c_float, _P, _P, C.c_int32, _P]),

@@ -77,6 +77,7 @@ struct hw1f_engine {
     std::vector<float> h_drift, h_sdrift;
 
     DevBuf<uint32_t> d_Jpow2;            // [kNumPow][800]
+    DevBuf<uint32_t> d_Jnib;             // [4][16][800]: J^(n 16^j), the nibble powers prep_lo_kernel applies
     DevBuf<uint32_t> d_W;                // window tables
     uint32_t W_hi_base = 0, W_n_hi = 0, W_L_log2 = 0;
     DevBuf<uint32_t> d_U;                // [n_runs][5][L]
@@ -101,7 +102,7 @@ struct hw1f_engine {
     // only when the parameters change)
     DevBuf<char> d_model;
     char* h_model = nullptr;
-    size_t model_bytes = 0;
+    size_t model_bytes = 0, model_off_emI = 0;
     bool model_cached = false;
     hw1f_params cached_p{};
     // FD arena: shifted drift tables and exp(-Im) of the sigma -/+ eps scenarios (slots 2, 3) in one device
@@ -119,6 +120,10 @@ struct hw1f_engine {
     DevBuf<double> d_gpart;
     char* h_res = nullptr;
     size_t res_area_bytes = 0, res_doubles = 0;
+    // the last single-scenario bond-curve launch whose block partials are still in d_partials (hw1f_bond_curve_ci)
+    bool ci_valid = false;
+    StreamGeom ci_geom{};
+    unsigned ci_blocks = 0;
     // peers attached with hw1f_comm_attach: the *_moments entry points all-reduce in their tail
     bool comm_on = false;
     CommDev comm{};
@@ -356,6 +361,9 @@ int ensure_tables(hw1f_engine* e)
     HW_CUDA(e, e->d_Jpow2.ensure(flat.size()));
     HW_CUDA(e, cudaMemcpyAsync(e->d_Jpow2.p, flat.data(), flat.size() * sizeof(uint32_t), cudaMemcpyHostToDevice,
                                e->stream));
+    const std::vector<uint32_t> nib = jump_tables().flat_seq_nibbles();
+    HW_CUDA(e, e->d_Jnib.ensure(nib.size()));
+    HW_CUDA(e, cudaMemcpyAsync(e->d_Jnib.p, nib.data(), nib.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, e->stream));
     HW_CUDA(e, cudaStreamSynchronize(e->stream));
     return HW1F_OK;
 }
@@ -402,6 +410,7 @@ int prepare_launch(hw1f_engine* e, const uint64_t* seeds, int n_runs, uint64_t f
 {
     HW_REQUIRE(e, n_runs >= 1 && n_runs <= kMaxRuns, "n_runs must be in [1,32]");
     HW_REQUIRE(e, n_paths >= 1, "n_paths must be >= 1");
+    e->ci_valid = false;   // the launch that follows overwrites the block partials
     HW_REQUIRE(e, first_path + n_paths >= first_path, "path range overflows 64 bits");
     HW_TRY(ensure_tables(e));
     const uint32_t L_log2 = pick_L_log2(n_paths);
@@ -434,7 +443,7 @@ int prepare_launch(hw1f_engine* e, const uint64_t* seeds, int n_runs, uint64_t f
     PlanJob no_job{};
     if (job) HW_CUDA(e, e->d_plans.ensure(4));
     // + 1: the plan block
-    prep_lo_kernel<<<prep_blocks + 1, 256, 0, e->stream>>>(L->seeds, n_runs, L_log2, e->d_Jpow2.p, e->d_U.p, model_dev(e),
+    prep_lo_kernel<<<prep_blocks + 1, 256, 0, e->stream>>>(L->seeds, n_runs, L_log2, e->d_Jnib.p, e->d_U.p, model_dev(e),
                                                           job ? *job : no_job);
     HW_TRY(check_launch(e, "prep_lo_kernel"));
 
@@ -869,6 +878,12 @@ void zbc_algebra(const double mom[5], uint64_t n_paths_total, float P0S2, int32_
     r->se_cv = (var_cv > 0) ? sqrt(var_cv / (2.0 * n)) : 0.0;
     r->ci95_lo = r->price_cv_f64 - 1.959963984540054 * r->se_cv;
     r->ci95_hi = r->price_cv_f64 + 1.959963984540054 * r->se_cv;
+    // beta*, rho and their standard errors from the same five moments: regression slope and Fisher's formula with one
+    // degree of freedom per antithetic pair
+    const double rho = (vxx > 0 && vyy > 0) ? cxy / sqrt(vxx * vyy) : 0.0;
+    r->corr_f64 = rho;
+    r->beta_se = (vyy > 0 && n > 2) ? sqrt((1.0 - rho * rho) * vxx / (vyy * (n - 2.0))) : 0.0;
+    r->corr_se = (n > 3) ? (1.0 - rho * rho) / sqrt(n - 3.0) : 0.0;
 }
 
 // loads every simulation kernel and opts it in to the full shared-memory carve-out (once per engine)
@@ -1015,7 +1030,7 @@ int hw1f_engine_destroy(hw1f_engine* e)
     if (!e) return HW1F_OK;
     cudaSetDevice(e->device);
     cudaStreamSynchronize(e->stream);
-    e->d_Jpow2.release(); e->d_W.release(); e->d_U.release();
+    e->d_Jpow2.release(); e->d_Jnib.release(); e->d_W.release(); e->d_U.release();
     for (auto& d : e->d_drift) d.release();
     e->d_mkt.release(); e->d_center.release(); e->d_plans.release();
     for (auto& d : e->d_emI) d.release(); e->d_partials.release(); e->d_moments.release(); e->d_state.release();
@@ -1104,6 +1119,7 @@ int hw1f_set_model(hw1f_engine* e, const hw1f_params* p)
     const size_t off_c = off_d1 + align((size_t)(n + 2) * sizeof(float2));
     const size_t off_e = off_c + align((size_t)nm * sizeof(float));
     const size_t total = off_e + align((size_t)nm * sizeof(float));
+    e->model_off_emI = off_e;
     const bool same = e->model_cached && memcmp(&e->cached_p, p, sizeof(*p)) == 0 && total == e->model_bytes;
     if (!same) {
         // an upload enqueued by an earlier call may still read the pinned mirror
@@ -1277,6 +1293,9 @@ static int curve_run(hw1f_engine* e, hw1f_rng* rng, double* d_moments, const Fin
     const ScenDev sc = scen_dev(e, e->p.sigma, e->sig_st, 0);
     HW_TRY(launch_curve(e, L, &sc, 1, d_moments, 0, fin));
     rng->offset += (uint64_t)e->p.n_steps;
+    e->ci_valid = true;
+    e->ci_geom = L.g;
+    e->ci_blocks = L.grid_x;
     return HW1F_OK;
 }
 
@@ -1340,6 +1359,78 @@ int hw1f_bond_curve(hw1f_engine* e, hw1f_rng* rng, float* P, float* f, float* P_
     HW_TRY(wait_results(e));
     HW_TRY(read_curve(e, 0, 0, P, f, P_se));
     if (sim_ms) HW_CUDA(e, cudaEventElapsedTime(sim_ms, e->ev0, e->ev1));
+    return HW1F_OK;
+}
+
+// Standard errors of f(0,T) and theta(T) (and, as a cross-check, of P) by batch means over the simulation blocks of
+// the last bond-curve launch + the delta method through compute_average_and_forward (market_data.cuh:101-127) and
+// recover_theta (src/2:14-35): f and theta are linear in ln P of up to five neighbouring maturities.
+int hw1f_bond_curve_ci(hw1f_engine* e, float* f_se, float* theta_se, float* P_se_batch)
+{
+    HW_TRY(require_model(e));
+    HW_CUDA(e, cudaSetDevice(e->device));
+    if (!e->ci_valid) {
+        e->err = "hw1f_bond_curve_ci needs a preceding bond-curve launch on this engine (its block partials)";
+        return HW1F_ERR_INVALID;
+    }
+    const int nm = e->p.n_mat;
+    const unsigned B = e->ci_blocks;
+    if (B < 8) {
+        e->err = "batch-means confidence intervals need at least 8 simulation blocks (8192 subsequences)";
+        return HW1F_ERR_UNSUPPORTED;
+    }
+    DevBuf<double> buf;
+    HW_CUDA(e, buf.ensure((size_t)(kCiLags + 1) * nm));
+    curve_batch_cov_kernel<<<nm, 256, 0, e->stream>>>(e->d_partials.p, (int)B, 2 * nm, nm, e->ci_geom, buf.p);
+    int st = check_launch(e, "curve_batch_cov_kernel");
+    std::vector<double> h((size_t)(kCiLags + 1) * nm);
+    if (st == HW1F_OK) st = download(e, h.data(), buf.p, h.size() * sizeof(double));
+    buf.release();
+    HW_TRY(st);
+    const double n = (double)e->ci_geom.n_paths, bias = (double)B / (double)(B - 1);
+    const float* emI = reinterpret_cast<const float*>(e->h_model + e->model_off_emI);
+    // P_m = (sum_b S_b[m] + n c_m) / (2n), c_m = 2 exp(-Im) (both arithmetic modes centre on it)
+    std::vector<double> P(nm);
+    for (int m = 0; m < nm; ++m) P[m] = (m == 0) ? 1.0 : (h[(size_t)kCiLags * nm + m] + n * 2.0 * (double)emI[m]) / (2.0 * n);
+    // covariance of ln P_i, ln P_j for |i - j| < kCiLags
+    auto cov_ln = [&](int i, int j) {
+        const int lo = i < j ? i : j, l = i < j ? j - i : i - j;
+        if (l >= kCiLags) return 0.0;
+        return bias * h[(size_t)l * nm + lo] / (4.0 * n * n * P[i] * P[j]);
+    };
+    // f = A ln P (two entries per row), theta = (D + a) f + const
+    const double dT = (double)e->spacing, a = (double)e->p.a;
+    std::vector<std::vector<std::pair<int, double>>> A(nm), Th(nm);
+    for (int m = 0; m < nm; ++m) {
+        const int first = (m == 0) ? 0 : m - 1, last = (m == nm - 1) ? nm - 1 : m + 1;
+        const double c = -(((m == 0) || (m == nm - 1)) ? 1.0 : 0.5) / dT;
+        A[m] = {{last, c}, {first, -c}};
+    }
+    auto add_row = [&](std::vector<std::pair<int, double>>& dst, const std::vector<std::pair<int, double>>& src, double w) {
+        for (const auto& kv : src) {
+            bool found = false;
+            for (auto& d : dst)
+                if (d.first == kv.first) { d.second += w * kv.second; found = true; break; }
+            if (!found) dst.push_back({kv.first, w * kv.second});
+        }
+    };
+    for (int i = 0; i < nm; ++i) {
+        if (i == 0) { add_row(Th[i], A[1], 1.0 / dT); add_row(Th[i], A[0], -1.0 / dT); }
+        else if (i == nm - 1) { add_row(Th[i], A[i], 1.0 / dT); add_row(Th[i], A[i - 1], -1.0 / dT); }
+        else { add_row(Th[i], A[i + 1], 0.5 / dT); add_row(Th[i], A[i - 1], -0.5 / dT); }
+        add_row(Th[i], A[i], a);
+    }
+    auto var_of = [&](const std::vector<std::pair<int, double>>& row) {
+        double v = 0.0;
+        for (const auto& x : row)
+            for (const auto& y : row) v += x.second * y.second * cov_ln(x.first, y.first);
+        return v > 0.0 ? v : 0.0;
+    };
+    for (int m = 0; m < nm; ++m) {
+        if (f_se) f_se[m] = (float)sqrt(var_of(A[m]));
+        if (theta_se) theta_se[m] = (float)sqrt(var_of(Th[m]));
+        if (P_se_batch) P_se_batch[m] = (float)(P[m] * sqrt(cov_ln(m, m) > 0 ? cov_ln(m, m) : 0.0));
+    }
     return HW1F_OK;
 }
 

@@ -156,7 +156,7 @@ __global__ void plan_job_kernel(ModelDev md, PlanJob job) { run_plan_job(md, job
 // releases it at once (its prologue overlaps the table build) and the dependent waits with griddepcontrol.wait
 // before it touches U or the plans.
 __global__ void __launch_bounds__(256)
-prep_lo_kernel(SeedArgs seeds, int n_runs, uint32_t L_log2, const uint32_t* __restrict__ Jpow2,
+prep_lo_kernel(SeedArgs seeds, int n_runs, uint32_t L_log2, const uint32_t* __restrict__ Jnib,
                uint32_t* __restrict__ U, ModelDev md, PlanJob job)
 {
     asm volatile("griddepcontrol.launch_dependents;");
@@ -173,8 +173,13 @@ prep_lo_kernel(SeedArgs seeds, int n_runs, uint32_t L_log2, const uint32_t* __re
     uint32_t v[5];
 #pragma unroll
     for (int w = 0; w < 5; ++w) v[w] = seeds.s[run].v0[w];
-    for (uint32_t k = 0; k < L_log2; ++k)
-        if ((lo >> k) & 1u) warp_matvec(Jpow2 + (size_t)k * 800, v, lane);
+    // J^lo as the product of at most four nibble powers J^(n 16^j) (L <= 2^16): a dependent chain of four table
+    // look-ups instead of one per set bit of lo
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const uint32_t n = (lo >> (4 * j)) & 15u;
+        if (n) warp_matvec(Jnib + (size_t)(j * 16 + n) * 800, v, lane);
+    }
     if (lane < 5) {
         uint32_t out = v[0];
         if (lane == 1) out = v[1];

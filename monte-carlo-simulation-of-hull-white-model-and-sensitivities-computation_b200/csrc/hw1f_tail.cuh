@@ -197,6 +197,81 @@ inline size_t tail_smem_bytes(int nq, int n_mat)
     return (a > b ? a : b) + 16;
 }
 
+// ---- confidence intervals of f(0,T) and theta(T): batch means over the simulation blocks --------------------------
+// The curve kernels keep sum d and sum d^2 per maturity (d = p0 - c_m), which gives the standard error of P but not of
+// quantities that DIFFERENCE neighbouring maturities (f = -d ln P / dT, theta = df/dT + a f + ...): those need the
+// covariance of P at nearby maturities.  Every simulation block is an independent batch of subsequences, so the
+// covariance band comes from the per-block partial sums the reduction tree already holds, at no cost to the hot loop:
+//   C[l][m] = sum_b (S_b[m] - n_b mu_m)(S_b[m+l] - n_b mu_(m+l)),  l = 0..kCiLags-1,
+// S_b[m] = partials[b][m] (block sum of d_m), n_b = subsequences block b simulated, mu_m = sum_b S_b[m] / n.
+// Also stores tot[m] = sum_b S_b[m].  Grid: n_mat blocks of 256 threads.  out: [kCiLags + 1][n_mat] doubles.
+constexpr int kCiLags = 5;
+
+__device__ __forceinline__ unsigned long long block_subsequences(const StreamGeom& g, unsigned b, unsigned grid)
+{
+    unsigned long long n = 0;
+    for (unsigned long long c = b; c < g.n_chunks; c += grid) {
+        const unsigned long long lo = (g.chunk0 + c) << kChunkLog2, hi = lo + kChunk;
+        const unsigned long long a = lo > g.first_path ? lo : g.first_path;
+        const unsigned long long e = hi < g.first_path + g.n_paths ? hi : g.first_path + g.n_paths;
+        if (e > a) n += e - a;
+    }
+    return n;
+}
+
+__global__ void __launch_bounds__(256)
+curve_batch_cov_kernel(const double* __restrict__ partials, int n_blocks, int stride, int n_mat, StreamGeom g,
+                       double* __restrict__ out)
+{
+    __shared__ double sh[kCiLags + 1][256];
+    const int m = blockIdx.x, tid = threadIdx.x;
+    const double n_all = (double)g.n_paths;
+    // pass 1: totals of columns m .. m+kCiLags-1
+    double t[kCiLags];
+#pragma unroll
+    for (int l = 0; l < kCiLags; ++l) t[l] = 0.0;
+    for (int b = tid; b < n_blocks; b += 256)
+#pragma unroll
+        for (int l = 0; l < kCiLags; ++l)
+            if (m + l < n_mat) t[l] += partials[(size_t)b * stride + m + l];
+#pragma unroll
+    for (int l = 0; l < kCiLags; ++l) sh[l][tid] = t[l];
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (tid < o)
+#pragma unroll
+            for (int l = 0; l < kCiLags; ++l) sh[l][tid] += sh[l][tid + o];
+        __syncthreads();
+    }
+    double mu[kCiLags];
+#pragma unroll
+    for (int l = 0; l < kCiLags; ++l) mu[l] = sh[l][0] / n_all;
+    const double tot_m = sh[0][0];
+    __syncthreads();
+    // pass 2: centred cross products
+    double c[kCiLags];
+#pragma unroll
+    for (int l = 0; l < kCiLags; ++l) c[l] = 0.0;
+    for (int b = tid; b < n_blocks; b += 256) {
+        const double nb = (double)block_subsequences(g, (unsigned)b, (unsigned)n_blocks);
+        const double d0 = partials[(size_t)b * stride + m] - nb * mu[0];
+#pragma unroll
+        for (int l = 0; l < kCiLags; ++l)
+            if (m + l < n_mat) c[l] += d0 * (partials[(size_t)b * stride + m + l] - nb * mu[l]);
+    }
+#pragma unroll
+    for (int l = 0; l < kCiLags; ++l) sh[l][tid] = c[l];
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (tid < o)
+#pragma unroll
+            for (int l = 0; l < kCiLags; ++l) sh[l][tid] += sh[l][tid + o];
+        __syncthreads();
+    }
+    if (tid < kCiLags) out[(size_t)tid * n_mat + m] = sh[tid][0];
+    if (tid == 0) out[(size_t)kCiLags * n_mat + m] = tot_m;
+}
+
 // the same publication step as a launch of its own: for moment vectors that were reduced by separate kernels
 // (reference-order mode) or that come back from an external all-reduce (hw1f_*_finish).  One block per run.
 __global__ void __launch_bounds__(256) tail_publish_kernel(TailArgs ta, ModelDev md, int nqc)

@@ -75,6 +75,20 @@ static std::vector<uint32_t> flatten(const std::vector<BitMatrix>& ms)
 std::vector<uint32_t> JumpTables::flat_step() const { return flatten(step_pow2); }
 std::vector<uint32_t> JumpTables::flat_seq() const { return flatten(seq_pow2); }
 
+std::vector<uint32_t> JumpTables::flat_seq_nibbles() const
+{
+    std::vector<BitMatrix> ms;
+    ms.reserve(64);
+    for (int j = 0; j < 4; ++j)
+        for (int n = 0; n < 16; ++n) {
+            BitMatrix m = BitMatrix::identity();
+            for (int b = 0; b < 4; ++b)
+                if ((n >> b) & 1) m = seq_pow2[4 * j + b].after(m);   // powers of one matrix commute
+            ms.push_back(m);
+        }
+    return flatten(ms);
+}
+
 const JumpTables& jump_tables()
 {
     static const JumpTables t;

@@ -35,6 +35,9 @@ struct JumpTables {
     // flat uint32 images for upload: [kNumPow][160][5]
     std::vector<uint32_t> flat_step() const;
     std::vector<uint32_t> flat_seq() const;
+    // J^(n * 16^j) for the four low nibbles j of a subsequence index, n = 0..15 (n = 0: identity): flat
+    // [4][16][160][5].  prep_lo_kernel applies at most four of them in a row instead of one J^(2^k) per set bit.
+    std::vector<uint32_t> flat_seq_nibbles() const;
 };
 
 const JumpTables& jump_tables();  // process-wide singleton

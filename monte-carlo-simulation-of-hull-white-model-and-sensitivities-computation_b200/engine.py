@@ -199,6 +199,12 @@ class Engine:
                                                      _ptr(f), _ptr(se) if with_se else None))
         return {"P": P, "f": f, "P_se": se}
 
+    def bond_curve_ci(self):
+        """standard errors of f(0,T), theta(T) (and P, by batch means) for the last bond-curve launch on this engine"""
+        f_se, th_se, p_se = (np.zeros(self.n_mat, np.float32) for _ in range(3))
+        self._check(self._lib.hw1f_bond_curve_ci(self._h, _ptr(f_se), _ptr(th_se), _ptr(p_se)))
+        return {"f_se": f_se, "theta_se": th_se, "P_se_batch": p_se}
+
     # -- Q2a: recover_theta (src/2_option_pricing.cu:14-35,70-102) --
     def theta_calibrate(self, f):
         f = _f32(f, self.n_mat)

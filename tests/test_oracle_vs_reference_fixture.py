@@ -57,7 +57,7 @@ def test_zbc_moments_of_real_kernel(oracle, ref):
     r = oracle.zbc_algebra(mom, 2 * N, float(P[100]))
     assert r["price_cv"] == pytest.approx(ref["zbc_price_cv"], rel=1e-5)
     assert r["mean_X"] == pytest.approx(ref["zbc_mean_X"], rel=1e-5)
-    assert r["beta"] == pytest.approx(ref["zbc_beta"], rel=5e-4)
+    assert r["beta"] == pytest.approx(ref["zbc_beta"], rel=1e-5)     # measured 2e-6 (two runs of the reference: 5.5e-7)
 
 
 def test_pathwise_vega_of_real_kernel(oracle, ref):
