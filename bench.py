@@ -668,6 +668,27 @@ def main():
                        "issue_frac": path_steps_per_step / world / (other_ms * 1e-3) * ALGO[other]["issue"] / issue_peak},
     }
 
+    # ---- steady state of the simulation kernel: time per wave of resident blocks, from two grids that are exact
+    # multiples of the resident capacity (launch ramp, seeding launch, reduction and the ragged last wave cancel) ----
+    steady = None
+    try:
+        cap = sm_count * 2                                   # resident 512-thread blocks = chunks of 1024 subsequences
+        t_by_waves = {}
+        for waves in (4, 8):
+            nn = cap * waves * 1024
+            ms = sorted(eng.bond_curve(hw.Rng(600 + i, nn))["sim_ms"] for i in range(7))[1:-1]
+            t_by_waves[waves] = sum(ms) / len(ms)
+        per_wave_ms = (t_by_waves[8] - t_by_waves[4]) / 4.0
+        ss_rate = cap * 1024 * 2.0 * n_steps / (per_wave_ms * 1e-3)
+        steady = {"ms_per_wave": per_wave_ms, "chunks_per_wave": cap, "value": ss_rate,
+                  "xu_frac": ss_rate * algo["xu"] / mufu, "fixed_ms_per_call": t_by_waves[4] - 4.0 * per_wave_ms,
+                  "note": "event-timed hw1f_bond_curve at 4 and 8 full waves of resident blocks; the difference is four "
+                          "waves of pure simulation (stream derivation and block partials included), the remainder the "
+                          "per-call fixed time (prep_lo_kernel, launch ramp, ragged drain, tail_kernel)"}
+    except Exception as exc:   # noqa: BLE001
+        steady = {"error": str(exc)}
+    roofline["steady_state"] = steady
+
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
         from oracle_lib import Oracle

@@ -8,6 +8,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -121,6 +122,7 @@ struct hw1f_engine {
     char* h_res = nullptr;
     size_t res_area_bytes = 0, res_doubles = 0;
     // the last single-scenario bond-curve launch whose block partials are still in d_partials (hw1f_bond_curve_ci)
+    bool seq_one_launch = true;          // hw1f_vega: the whole Q3 sequence as one simulation launch (HW1F_Q3_ONE_LAUNCH=0 disables)
     bool ci_valid = false;
     StreamGeom ci_geom{};
     unsigned ci_blocks = 0;
@@ -905,6 +907,7 @@ int init_kernels(hw1f_engine* e)
     HW_CUDA(e, opt_in(fast_kernel<0, 0, 1>, b));
     HW_CUDA(e, opt_in(fast_kernel<1, 1, 2>, b));
     HW_CUDA(e, opt_in(fast_kernel<1, 3, 2>, b));
+    HW_CUDA(e, opt_in((fast_kernel<2, 3, 1, 1, 1>), b));
     HW_CUDA(e, opt_in(zbc_sum_kernel<0>, b));
     HW_CUDA(e, opt_in(zbc_sum_kernel<1>, b));
     HW_CUDA(e, opt_in(zbc_sum_kernel<2>, b));
@@ -1016,6 +1019,7 @@ int hw1f_engine_create(int device, hw1f_engine** out)
         return HW1F_ERR_CUDA;
     }
     e->stream = e->own_stream;
+    if (const char* q = std::getenv("HW1F_Q3_ONE_LAUNCH")) e->seq_one_launch = q[0] != '0';
     if (init_kernels(e) != HW1F_OK) {
         std::fprintf(stderr, "hw1f_engine_create: %s\n", e->err.c_str());
         hw1f_engine_destroy(e);
@@ -1791,6 +1795,77 @@ int hw1f_vega(hw1f_engine* e, hw1f_rng* rng, float S1, float S2, float K, const 
         HW_TRY(hw1f_vega_pathwise(e, rng, S1, S2, K, P_mkt, f_mkt, n, out));     // normals [0,n)
         HW_TRY(hw1f_vega_fd(e, rng, S1, S2, K, P_mkt, f_mkt, eps, n, out));      // normals [n,2n)
         return hw1f_vega_fd_recalibrated(e, rng, S1, S2, K, eps, n, out);        // normals [2n,..)
+    }
+    const bool one_launch = e->mode == HW1F_MODE_DECOMPOSED && n > 0 && (n & 1) == 0 && (n % e->stride) == 0 &&
+                            rng->n_paths <= (1ull << 27) && e->seq_one_launch;
+    if (one_launch) {
+        // ONE pass over each subsequence's normals (fast_kernel SEQ): pathwise tangent on [off, off+n), both CRN bumps on
+        // [off+n, off+2n), the two recalibration curves on [off+2n, off+2n+N_STEPS) with the noise state parked at step
+        // n of that window; the tail kernel reduces, finalises both recalibrated curves and their bond plans; the two
+        // recalibrated prices come from the parked state.  Five launches (jump table, simulation, tail, prices, tail)
+        // instead of eleven, one stream derivation per subsequence instead of three.  Same draw windows, same results.
+        HW_CUDA(e, e->d_moments.ensure(4 * (size_t)nm * kMaxRuns));
+        HW_CUDA(e, e->d_mkt.ensure(4 * (size_t)nm));
+        const float sig_m = e->p.sigma - eps, sig_p = e->p.sigma + eps;
+        HW_TRY(upload_fd_tables(e, sig_m, sig_p));
+        const ScenDev base = scen_dev(e, e->p.sigma, e->sig_st, 0);
+        const ScenDev three[3] = {base, scen_dev(e, sig_m, host_sig_st(e->p, sig_m), 2),
+                                  scen_dev(e, sig_p, host_sig_st(e->p, sig_p), 3)};
+        ScenDev rc[2] = {scen_dev(e, sig_m, host_sig_st(e->p, sig_m), 0), scen_dev(e, sig_p, host_sig_st(e->p, sig_p), 0)};
+        HW_TRY(warm_geometry(e, rng));
+        HW_CUDA(e, cudaEventRecord(e->ev0, e->stream));
+        const PlanJob job = plan_job_host(e, three, 3, S1, S2, P_mkt, f_mkt);
+        Launch L;
+        HW_TRY(prepare_launch(e, &rng->seed, 1, rng->first_path, rng->n_paths, rng->offset, &L, &job));
+        const int nq = 4 * nm + 18;
+        HW_CUDA(e, e->d_partials.ensure((size_t)L.grid_x * nq));
+        HW_CUDA(e, e->d_state.ensure((size_t)L.g.n_chunks * kChunk));
+        const FastScen c0 = fast_scen(e, rc[0].sig_st, 0, 0), c1 = fast_scen(e, rc[1].sig_st, 0, 0);
+        const FastScen zb = fast_scen(e, base.sig_st, 0, n), zm = fast_scen(e, three[1].sig_st, 2, n),
+                       zp = fast_scen(e, three[2].sig_st, 3, n);
+        const FastTangent tg = fast_tangent(e, n);
+        const size_t smem = smem_fast(e, 2);
+        HW_TRY(set_smem(e, (fast_kernel<2, 3, 1, 1, 1>), smem));
+        HW_CUDA(e, launch_k(fast_kernel<2, 3, 1, 1, 1>, dim3(L.grid_x), kThreads, smem, e->stream, true, L.g, L.seeds,
+                            model_dev(e), c0, c1, zb, zm, zp, tg, e->d_plans.p, n, 0, K, e->d_partials.p, e->d_state.p));
+        HW_TRY(check_launch(e, "fast_kernel<q3 sequence>"));
+        Finish fc;
+        fc.host_mom = res_mom(e, 0);          // [4 nm curve sums][5 unused][pathwise 3][FD- 5][FD+ 5]
+        fc.epi = true;
+        fc.n_total = rng->n_paths;
+        fc.dev_curve = e->d_mkt.p;
+        fc.host_curve = res_curve(e, 0);
+        fc.plan = plan_job_dev(e, rc, 2, S1, S2);
+        HW_TRY(launch_tail(e, L, L.g.n_paths, nq, 2, c0.emI, c1.emI, 2.0f, e->d_moments.p, nq, 18, fc));
+        Finish fz;
+        fz.host_mom = res_mom(e, 1);
+        HW_TRY(launch_zbc_from_state(e, L, rc, n, K, e->d_moments.p + nq, fz));
+        HW_CUDA(e, cudaEventRecord(e->ev1, e->stream));
+        rng->offset += 3 * (uint64_t)n;
+        HW_TRY(wait_results(e));
+        const double* ext = res_mom(e, 0) + 4 * (size_t)nm;
+        HW_TRY(require_finite(e, ext, 18));
+        HW_TRY(require_finite(e, res_mom(e, 1), 10));
+        const float P0S2 = P_mkt[nm - 1];
+        out->n_steps_S1 = n;
+        pathwise_result(ext + 5, rng->n_paths, out);
+        out->price_minus = zbc_price_cv(ext + 8, rng->n_paths, P0S2);
+        out->price_plus = zbc_price_cv(ext + 13, rng->n_paths, P0S2);
+        out->vega_fd = (out->price_plus - out->price_minus) / (2.0f * eps);                     // src/3:443
+        {
+            const float* cur = res_curve(e, 0);
+            const float P0S2_rc[2] = {cur[nm - 1], cur[3 * (size_t)nm + nm - 1]};
+            out->price_minus_recal = zbc_price_cv(res_mom(e, 1), rng->n_paths, P0S2_rc[0]);
+            out->price_plus_recal = zbc_price_cv(res_mom(e, 1) + 5, rng->n_paths, P0S2_rc[1]);
+            out->vega_fd_recal = (out->price_plus_recal - out->price_minus_recal) / (2.0f * eps);   // src/3:513
+        }
+        float ms = 0.f;   // one launch: apportioned by the normals each estimator consumed
+        HW_CUDA(e, cudaEventElapsedTime(&ms, e->ev0, e->ev1));
+        const float tot = (float)(2 * n + e->p.n_steps);
+        out->ms_pathwise = ms * (float)n / tot;
+        out->ms_fd = ms * (float)n / tot;
+        out->ms_fd_recal = ms * (float)e->p.n_steps / tot;
+        return HW1F_OK;
     }
     // The three estimators of the reference's main() (src/3:697-834) enqueued back to back -- same draw windows and
     // same results as hw1f_vega_pathwise + hw1f_vega_fd + hw1f_vega_fd_recalibrated -- seven launches in all (three

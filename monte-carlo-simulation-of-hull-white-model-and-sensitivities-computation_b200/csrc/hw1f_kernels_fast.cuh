@@ -48,6 +48,25 @@ struct FastTangent {
 #ifndef HW1F_FAST_COSH_POLY
 #define HW1F_FAST_COSH_POLY 1
 #endif
+#ifndef HW1F_RHO_POS
+#define HW1F_RHO_POS 2               // position of the decay residual in the five-pair group (any is equivalent to first order;
+                                     // A/B of all five x HW1F_FIXED_HALF: profiles/r02_ab_variants.txt)
+#endif
+#ifndef HW1F_MLOOP_UNROLL
+#define HW1F_MLOOP_UNROLL 0          // 0: compiler's choice for the maturity loop
+#endif
+#ifndef HW1F_POLY_ESTRIN
+#define HW1F_POLY_ESTRIN 0           // 1: Estrin evaluation of the save-point polynomial (shorter dependency chain)
+#endif
+#ifndef HW1F_VOTE_EVERY
+#define HW1F_VOTE_EVERY 1            // A/B: profiles/r02_ab_variants.txt
+#endif
+#ifndef HW1F_VOTE_THRESHOLD
+#define HW1F_VOTE_THRESHOLD 0.8f
+#endif
+#ifndef HW1F_FIXED_HALF
+#define HW1F_FIXED_HALF 1            // 1: a code path for the default save stride (10 steps = one five-pair group)
+#endif
 
 struct FastState {
     float2 h, W;
@@ -89,7 +108,12 @@ __device__ __forceinline__ constexpr int ext_zbc(int s) { return s == 0 ? 0 : 5 
 template <int NZBC, int PW>
 __device__ __forceinline__ constexpr int ext_pw() { return NZBC > 0 ? 5 : 0; }
 
-template <int NCUR, int NZBC, int PW, int DUMP = 0>
+// SEQ   : 1 = the whole Q3 sequence of the reference's main() (src/3:697-834) in ONE pass over each subsequence's normals:
+//         pathwise tangent on normals [0, n), then both CRN finite-difference bumps (scenarios 1, 2: zs1/zs2, plans[1],
+//         plans[2]) on [n, 2n), then the two recalibration curves (cs0, cs1) on [2n, 2n + n_steps) with the noise state
+//         parked at step n of that window (DUMP) -- one stream derivation instead of three.  Instantiated as
+//         fast_kernel<2, 3, 1, 1, 1>; scenario 0's five ZBC slots stay zero.
+template <int NCUR, int NZBC, int PW, int DUMP = 0, int SEQ = 0>
 #ifndef HW1F_FAST_MIN_BLOCKS
 #define HW1F_FAST_MIN_BLOCKS 2   // A/B in profiles/r01_ab_variants_decomposed.txt: 512 threads x 2 blocks (64 regs) is best
 #endif
@@ -124,6 +148,7 @@ fast_kernel(StreamGeom g, SeedArgs seeds, ModelDev md, FastScen cs0, FastScen cs
         }
     }
     if (kS1 > 0 && tid < kS1) bext[tid] = 0.0;
+    if (SEQ && tid < kWarps * 5) wext[tid / 5][tid % 5] = 0.0;   // scenario 0's ZBC slots are not used by the sequence
 
     const float2 e2 = splat(md.exp_adt), ee2 = splat(md.exp_2adt);
     const int half = md.stride >> 1;
@@ -158,7 +183,7 @@ fast_kernel(StreamGeom g, SeedArgs seeds, ModelDev md, FastScen cs0, FastScen cs
             const float2 b = add2(sn, cs);
             // the residual of the group's five RN(e^2) decays goes in at position 1 (any position is equivalent to
             // first order; ptxas' schedule of this one is 1.7 % faster than of the others, profiles/r01_ab_variants_decomposed.txt)
-            if (j == 1) st.h = fma2(st.h, splat(md.rho5), st.h);
+            if (j == HW1F_RHO_POS) st.h = fma2(st.h, splat(md.rho5), st.h);
             st.h = fma2(s, a, mul2(st.h, ee2));
             st.W = fma2(s, b, st.W);
         };
@@ -182,6 +207,7 @@ fast_kernel(StreamGeom g, SeedArgs seeds, ModelDev md, FastScen cs0, FastScen cs
             }
         };
 
+        bool big = false;   // a lane of this warp is near the validity limit of the save-point polynomial
         auto save_curve = [&](int m) {
 #pragma unroll
             for (int s = 0; s < NCUR; ++s) {
@@ -194,17 +220,35 @@ fast_kernel(StreamGeom g, SeedArgs seeds, ModelDev md, FastScen cs0, FastScen cs
                 // z = c q = (c qA) W - (c qB) h
                 const float2 z = fma2(st.W, splat(s ? zA1 : zA0), mul2(st.h, splat(s ? zB1 : zB0)));
                 float2 d2;
+#if HW1F_VOTE_EVERY > 1
+                // |z| is re-examined every HW1F_VOTE_EVERY-th save point against a lower threshold: over that many
+                // save points z moves by ~0.09 sqrt(HW1F_VOTE_EVERY / 10) (one sd), and the polynomial degrades
+                // gracefully (relative truncation 3e-8 at |z| = 1.2, 4e-6 at |z| = 2)
+                if ((m % HW1F_VOTE_EVERY) == 1 || s > 0) {
+                    if (s == 0) big = __any_sync(0xffffffffu, fmaxf(fabsf(z.x), fabsf(z.y)) > HW1F_VOTE_THRESHOLD);
+                }
+                if (big) {
+#else
                 if (__any_sync(0xffffffffu, fmaxf(fabsf(z.x), fabsf(z.y)) > 1.2f)) {
+#endif
                     const float2 y = mul2(z, splat(kLog2e));
                     const float2 ep = make_float2(mufu_ex2(y.x), mufu_ex2(y.y));
                     const float2 en = make_float2(mufu_ex2(-y.x), mufu_ex2(-y.y));
                     d2 = add2(add2(ep, en), splat(-2.0f));
                 } else {
                     const float2 w = mul2(z, z);
+#if HW1F_POLY_ESTRIN
+                    const float2 w2 = mul2(w, w);
+                    const float2 lo = fma2(w, splat(1.0f / 12.0f), splat(1.0f));
+                    const float2 mid = fma2(w, splat(1.0f / 20160.0f), splat(1.0f / 360.0f));
+                    const float2 hi = mul2(w2, splat(1.0f / 1814400.0f));
+                    const float2 pl = fma2(w2, add2(mid, hi), lo);
+#else
                     float2 pl = fma2(w, splat(1.0f / 1814400.0f), splat(1.0f / 20160.0f));
                     pl = fma2(pl, w, splat(1.0f / 360.0f));
                     pl = fma2(pl, w, splat(1.0f / 12.0f));
                     pl = fma2(pl, w, splat(1.0f));
+#endif
                     d2 = mul2(w, pl);
                 }
                 float2 dv = mul2(d2, splat(emI[s * n_mat + m]));
@@ -220,11 +264,12 @@ fast_kernel(StreamGeom g, SeedArgs seeds, ModelDev md, FastScen cs0, FastScen cs
             }
         };
 
-        auto eval_S1 = [&]() {
+        auto eval_S1 = [&](bool do_zbc, bool do_pw) {
             const float2 q = st.q(md.qA, md.qB);
             const double mA = t.validA ? 1.0 : 0.0, mB = t.validB ? 1.0 : 0.0;
 #pragma unroll
-            for (int s = 0; s < NZBC; ++s) {
+            for (int s = (SEQ ? 1 : 0); s < NZBC; ++s) {
+                if (!do_zbc) break;
                 const FastScen z = (s == 0) ? zs0 : (s == 1 ? zs1 : zs2);
                 float2 mom5[5];
                 fast_zbc_mom5(st.h, q, z, plans[s], K, mom5);
@@ -234,7 +279,7 @@ fast_kernel(StreamGeom g, SeedArgs seeds, ModelDev md, FastScen cs0, FastScen cs
                     if (lane == 0) wext[warp][ext_zbc<NZBC, PW>(s) + k] = w;
                 }
             }
-            if (PW) {
+            if (PW && do_pw) {
                 const BondPlan pl = plans[0];
                 const FastScen z = zs0;
                 const float2 dr = mul2(st.h, splat(z.sg)), dI = mul2(q, splat(z.c));
@@ -274,10 +319,30 @@ fast_kernel(StreamGeom g, SeedArgs seeds, ModelDev md, FastScen cs0, FastScen cs
         };
 
         if (NCUR) {
+            if (SEQ) {   // n_steps_S1 even, normal offset even (checked on the host)
+                advance(n_steps_S1 >> 1);
+                eval_S1(false, true);          // pathwise tangent, normals [0, n)
+                st.h = splat(0.0f);
+                st.W = splat(0.0f);
+                advance(n_steps_S1 >> 1);
+                eval_S1(true, false);          // CRN finite-difference bumps, normals [n, 2n)
+                st.h = splat(0.0f);
+                st.W = splat(0.0f);
+            }
+#if HW1F_MLOOP_UNROLL == 2
+#pragma unroll 2
+#elif HW1F_MLOOP_UNROLL == 1
+#pragma unroll 1
+#endif
             for (int m = 1; m < n_mat; ++m) {
+#if HW1F_FIXED_HALF
+                if (half == 5) { run_pairs_parts<5>(t, pair, pairfn); pair += 5; }
+                else advance(half);
+#else
                 advance(half);
+#endif
                 save_curve(m);
-                if (kS1 > 0 && m == m_S1) eval_S1();
+                if (!SEQ && kS1 > 0 && m == m_S1) eval_S1(true, true);
                 if (DUMP && m == m_S1) {
                     float2* d = dump + ((size_t)run * g.n_chunks + chunk) * kChunk + tid;
                     const float2 q = st.q(md.qA, md.qB);
@@ -298,7 +363,7 @@ fast_kernel(StreamGeom g, SeedArgs seeds, ModelDev md, FastScen cs0, FastScen cs
                 one_pair(t, ns, nc);
                 step1(ns);
             }
-            eval_S1();
+            eval_S1(true, true);
         }
         __syncthreads();
         if (NCUR) {

@@ -1,10 +1,22 @@
 #!/bin/bash
-# A/B of kernel build variants on the GPU box: prints ms/step of the Q1 bench for each library
+# A/B of kernel build variants on the GPU box: Q1 bench ms/step (device-timed, end-to-end, sustained) plus the event
+# times of the ZBC pass and the wall time of the Q3 sequence for each library under <pkg>/lib/variants/
 PKG=monte-carlo-simulation-of-hull-white-model-and-sensitivities-computation_b200
 for lib in $PKG/lib/libhw1f.so $PKG/lib/variants/*.so; do
   for rep in 1 2; do
-    HW1F_LIB=$PWD/$lib python bench.py --steps 100 --warmup 5 --no-cpu-baseline 2>/dev/null | python -c "
+    HW1F_LIB=$PWD/$lib python bench.py --steps 100 --warmup 5 --no-cpu-baseline --no-workloads --no-scaling-run 2>/dev/null | python -c "
 import sys, json
-l = json.loads(sys.stdin.readline()); print('$lib'.split('/')[-1].ljust(22), 'ms/step %.4f' % l['ms_per_step'], 'value %.4e' % l['value'], 'e2e_ms %.4f' % l['e2e']['ms_per_step'], 'mhz', l['clocks']['sm_mhz'])"
+l = json.loads(sys.stdin.readline()); print('$lib'.split('/')[-1].ljust(22), 'ms/step %.4f' % l['ms_per_step'], 'value %.4e' % l['value'], 'e2e_ms %.4f' % l['e2e']['ms_per_step'], 'sustained %.4f' % l['sustained']['ms_per_step'], 'steady-state XU %.4f' % l['roofline']['steady_state']['xu_frac'], 'mhz', l['clocks']['sm_mhz'])"
   done
+  HW1F_LIB=$PWD/$lib python - <<'PY'
+import time, hw1f_b200 as hw
+N = 1 << 20
+eng = hw.Engine(device=0)
+c = eng.bond_curve(hw.Rng(1234, N)); P, f = c["P"], c["f"]
+z = sorted(eng.zbc_cv(hw.Rng(i, N), P, f, n_steps_S1=500)["sim_ms"] for i in range(25))[5:-5]
+for i in range(3): eng.vega(hw.Rng(i, N), P, f, n_steps_S1=500)
+t0 = time.perf_counter()
+for i in range(20): eng.vega(hw.Rng(50 + i, N), P, f, n_steps_S1=500)
+print("    zbc event ms %.4f   q3 sequence wall ms %.4f" % (sum(z) / len(z), (time.perf_counter() - t0) * 1e3 / 20))
+PY
 done
