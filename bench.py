@@ -49,7 +49,7 @@ def workload_string(paths_log2=N_PATHS_LOG2, n_steps=1000, n_mat=101):
 
 
 # committed `ncu --set full` summaries of the dominant kernel per arithmetic mode (tools/ncu_summary.py)
-NCU_CAPTURE = {"decomposed": "profiles/r01_ncu_full_fast_kernel_v3.csv",
+NCU_CAPTURE = {"decomposed": "profiles/r02_ncu_full_fast_kernel.csv",
                "reference_order": "profiles/r01_ncu_full_bond_curve_v3.csv"}
 
 ALGO = {

@@ -120,8 +120,20 @@ def census(instrs):
             mufu_kinds[op] = mufu_kinds.get(op, 0) + 1
     total = len(body)
     packed = counts.get("packed_fp32x2", 0)
+    # every loop that holds MUFU work, outermost last: the maturity loop of the curve kernels contains the five-pair group
+    # twice (a straight-line copy for the default save stride, HW1F_FIXED_HALF, and the general group loop counted above)
+    # plus the save point (5 shuffles, the polynomial, the exponential fall-back)
+    nest = []
+    for l2, h2 in sorted(loops, key=lambda x: x[1] - x[0]):
+        b2 = instrs[l2:h2 + 1]
+        n_m = sum(1 for _, op, _ in b2 if op.startswith("MUFU"))
+        if n_m:
+            nest.append({"range": [hex(instrs[l2][0]), hex(instrs[h2][0])], "instructions": len(b2), "mufu": n_m,
+                         "packed_fp32x2": sum(1 for _, op, _ in b2 if op.split(".")[0] in PACKED),
+                         "shuffles": sum(1 for _, op, _ in b2 if op.startswith("SHFL"))})
     return {"loop_address_range": [hex(instrs[lo][0]), hex(instrs[hi][0])], "instructions": total, "by_class": counts,
-            "mufu_kinds": mufu_kinds, "dispatch_cycles": total + packed, "xu_cycles": 8 * counts.get("mufu", 0)}
+            "mufu_kinds": mufu_kinds, "dispatch_cycles": total + packed, "xu_cycles": 8 * counts.get("mufu", 0),
+            "loops_with_mufu": nest}
 
 
 def main():
