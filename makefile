@@ -31,6 +31,10 @@ $(OUTDIRS):
 $(DRIVERS): %: src/$$(stem_$$*).cpp include/hw1f.h include/hw1f_driver.hpp $(ENGINE) | $(OUTDIRS)
 	$(CXX) $(CXXFLAGS) $< -o bin/$@ $(LDLIBS)
 
+# host overhead of the C ABI measured from C++ (tools/api_overhead.cpp)
+api_overhead: tools/api_overhead.cpp include/hw1f.h include/hw1f_driver.hpp $(ENGINE) | $(OUTDIRS)
+	$(CXX) $(CXXFLAGS) $< -o bin/$@ $(LDLIBS)
+
 $(addprefix run-,$(DRIVERS)): run-%: % | $(OUTDIRS)
 	CUDA_VISIBLE_DEVICES=$(GPU) ./bin/$*
 
@@ -47,4 +51,4 @@ clean:
 clean-all:
 	$(RM) -r $(OUTDIRS)
 
-.PHONY: all run-all analyze clean clean-all $(addprefix run-,$(DRIVERS))
+.PHONY: all run-all analyze clean clean-all api_overhead $(addprefix run-,$(DRIVERS))

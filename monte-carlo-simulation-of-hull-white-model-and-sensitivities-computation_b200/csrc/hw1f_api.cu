@@ -662,6 +662,7 @@ int make_tail(hw1f_engine* e, int n_runs, unsigned grid_x, uint64_t n_local, int
     if (fin.exchange && e->comm_on) {
         HW_REQUIRE(e, n_runs == 1, "the peer exchange works on single-run launches");
         HW_REQUIRE(e, ncur * 2 * e->p.n_mat + n_ext_out <= kCommMaxCount, "moment vector too long for the peer mailboxes");
+        if (*e->comm_epoch == 0xffffffffu) { e->err = "communicator exhausted (2^32 exchanges): create a new one"; return HW1F_ERR_COMM; }
         t->comm = e->comm;
         t->epoch = ++*e->comm_epoch;
     }

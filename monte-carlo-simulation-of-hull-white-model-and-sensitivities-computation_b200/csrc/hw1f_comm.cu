@@ -1,19 +1,18 @@
-// hw1f_comm.cu -- the path's single exchange step as an own kernel over NVLink peer memory.
+// hw1f_comm.cu -- host side of the path's single exchange step (device side: hw1f_comm.cuh).
 //
-// One process per GPU (torchrun).  Every rank owns a small mailbox in device memory that all peers
-// map through CUDA IPC.  hw1f_comm_allreduce enqueues ONE kernel on the engine's stream that
-//   1. posts this rank's moment vector (<= 256 doubles) into its slot of EVERY peer's mailbox
-//      (plain stores over NVLink / NVSwitch), fences at system scope and raises a per-slot flag;
-//   2. waits until all peers' flags for this epoch have arrived in the local mailbox (bounded spin:
-//      a lost peer sets an error flag instead of hanging the GPU);
-//   3. sums the slots in RANK ORDER, so the result is bit-identical on every rank and from run to run
-//      (NCCL's ring/tree order depends on the communicator).
-// Mailboxes are double-buffered by epoch parity: a rank can only reach epoch e+2 after every peer
-// has posted epoch e+1, i.e. after every peer finished reading epoch e.
+// One process per GPU (torchrun).  Every rank owns a small mailbox in device memory that all peers map through CUDA
+// IPC.  The all-reduce of the moment vector (<= 512 doubles) is done by ONE block: it posts the vector into its slot of
+// EVERY peer's mailbox as flagged 8-byte words (plain stores over NVLink / NVSwitch; every word carries the epoch, so
+// there is no fence and no separate flag), polls its own mailbox until every rank's words of this epoch have arrived
+// (bounded spin: a lost peer poisons the result with NaN and bumps a counter instead of hanging the GPU), and sums the
+// slots in RANK ORDER, so the result is bit-identical on every rank and from run to run (NCCL's ring/tree order
+// depends on the communicator).  Mailboxes are double-buffered by epoch parity.
 //
-// For a 1.6 KB payload the collective is pure latency; this kernel replaces NCCL's ~25 us
-// all-reduce by one NVLink round trip.  NCCL (torch.distributed) remains the plumbing for the
-// handle exchange and the fallback/verification path in bench.py.
+// hw1f_comm_attach hands the mailboxes to the engine: the tail kernel behind every *_moments simulation launch then
+// does the exchange itself (no launch between reduction and collective).  hw1f_comm_allreduce is the same device code
+// as a launch of its own.  For a 1.6 KB payload the collective is pure latency: one NVLink one-way trip here, ~23 us
+// for NCCL's all-reduce.  NCCL (torch.distributed) remains the plumbing for the handle exchange and the verification
+// path in bench.py.
 #include <cuda_runtime.h>
 
 #include <cstdio>
@@ -112,7 +111,8 @@ int hw1f_comm_allreduce(hw1f_comm* c, double* d_data, int32_t count)
     if (!c || !d_data || c->rank < 0) return HW1F_ERR_INVALID;
     if (count < 1 || count > kCommMaxCount) { c->err = "count must be in [1,512]"; return HW1F_ERR_INVALID; }
     cudaSetDevice(c->device);
-    ++c->epoch;   // shared with the engine's kernel tails when attached: one sequence of epochs per communicator
+    if (c->epoch == 0xffffffffu) { c->err = "communicator exhausted (2^32 exchanges): create a new one"; return HW1F_ERR_COMM; }
+    ++c->epoch;   // shared with the engine's tail kernels when attached: one sequence of epochs per communicator
     peer_allreduce_kernel<<<1, 256, 0, c->stream>>>(c->dev, d_data, count, c->epoch);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { c->err = std::string("peer_allreduce_kernel: ") + cudaGetErrorString(e); return HW1F_ERR_CUDA; }
