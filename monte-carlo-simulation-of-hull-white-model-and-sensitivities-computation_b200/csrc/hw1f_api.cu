@@ -922,11 +922,9 @@ int init_kernels(hw1f_engine* e)
     HW_CUDA(e, cudaFuncGetAttributes(&attr, tail_publish_kernel));
     HW_CUDA(e, cudaFuncGetAttributes(&attr, tail_kernel));
     HW_CUDA(e, cudaFuncGetAttributes(&attr, reduce_partials_kernel<double>));
-    HW_CUDA(e, cudaFuncGetAttributes(&attr, reduce_curve_kernel));
     HW_CUDA(e, cudaFuncGetAttributes(&attr, zbc_from_state_kernel<2>));
     HW_CUDA(e, cudaFuncGetAttributes(&attr, curve_epilogue_kernel));
     HW_CUDA(e, cudaFuncGetAttributes(&attr, theta_kernel));
-    HW_CUDA(e, cudaFuncGetAttributes(&attr, fused_uncenter_kernel));
     HW_CUDA(e, cudaFuncGetAttributes(&attr, sample_paths_kernel));
     HW_CUDA(e, cudaFuncGetAttributes(&attr, steps_probe_kernel));
     // ticket counters of the kernel tails (self-resetting: zeroed once), bond plans

@@ -1,19 +1,21 @@
 // hw1f_kernels.cuh -- the CUDA kernels of the HW1F engine (sm_100a).
 //
 // Thread mapping shared by every simulation kernel
-//   * one block owns kChunk = 512 consecutive RNG subsequences ("reference threads"),
+//   * one block owns kChunk = 1024 consecutive RNG subsequences ("reference threads"),
 //     aligned in ABSOLUTE path index, so all of them share the same high jump matrix;
-//   * one thread owns two of them, A = base + tid and B = base + tid + 256, and keeps both
+//   * one thread owns two of them, A = base + tid and B = base + tid + 512, and keeps both
 //     in the two lanes of packed FP32x2 registers (FFMA2/FADD2/FMUL2), which halves the
-//     issue slots of the recursion;
+//     instruction count of the recursion (not its dispatch cycles: a packed instruction holds
+//     the port for two);
 //   * the XORWOW state of a subsequence is re-derived in the prologue:
 //        v = J^(hi*L) * ( J^lo * T^offset * v0(seed) ),   path = hi*L + lo,
 //     the bracket comes from the per-launch table U (prep_lo_kernel), J^(hi*L) is applied as
 //     40 nibble look-ups into a 12.8 KB window table staged in shared memory.
 //   * time loop in registers, drift table in shared memory as duplicated float2 (one LDS.128
 //     feeds two steps of both lanes), Box-Muller phase static (no flag, no branch).
-//   * reductions: warp shuffle tree -> shared -> one partial per block -> reduce_partials_kernel
-//     (fixed order, double).  No atomics anywhere: results are bit-reproducible.
+//   * reductions: warp shuffle tree -> shared -> one double partial row per block -> tail_kernel
+//     (hw1f_tail.cuh: groups of blocks, then groups; fixed order, double).  No atomics anywhere:
+//     results are bit-reproducible.
 #pragma once
 #include "hw1f_device.cuh"
 
@@ -343,7 +345,7 @@ __device__ __forceinline__ void one_pair(ThreadStreams& t, float2& ns, float2& n
 // partials[run][block][nq] doubles, nq = NSCEN * 2 * n_mat: per scenario sum_m d, sum_m d^2 with
 // d = p0_m - c_m.  Centring (c_m = the noise-free value, host-computed) makes the float shuffle
 // trees lose nothing: the variance of p0 at short maturities is 1e-10 of its square and would
-// vanish in float32 otherwise.  reduce_curve_kernel undoes the centring in double.
+// vanish in float32 otherwise.  tail_kernel (hw1f_tail.cuh) undoes the centring in double.
 // Blocks stride over chunks; per-warp float trees -> shared floats -> double block accumulators.
 template <int NSCEN>
 __global__ void __launch_bounds__(kThreads, (NSCEN > 1 ? 1 : HW1F_MIN_BLOCKS))
@@ -630,7 +632,8 @@ pathwise_kernel(StreamGeom g, SeedArgs seeds, ModelDev md, ScenDev sc, const Bon
 }
 
 // =================================================================================================
-// second level of the deterministic tree: moments[run][q] = sum over blocks (fixed order, double)
+// plain block-sum kernel: moments[run][q] = sum over blocks (fixed order, double).  The simulation launches are
+// finished by tail_kernel (hw1f_tail.cuh); this one remains for the reduction benchmark's deterministic method
 // =================================================================================================
 // partials[run][block][stride]; sums entries q = 0..gridDim.x-1 -> moments[run*out_stride + q]
 template <class T>
@@ -651,44 +654,6 @@ reduce_partials_kernel(const T* __restrict__ partials, int n_blocks, int stride,
         __syncthreads();
     }
     if (tid == 0) moments[(size_t)run * out_stride + q] = sh[0];
-}
-
-// curve variant: block (m, run*NSCEN+s) sums sum_d and sum_d2 of maturity m and undoes the centring
-// with c_m = center_scale * center[m]:
-//   sum p0 = sum d + n c,   sum p0^2 = sum d^2 + 2 c sum d + n c^2      (double)
-// partials[run][block][stride] with the curve block of scenario s at offset s*2*n_mat
-__global__ void __launch_bounds__(256)
-reduce_curve_kernel(const double* __restrict__ partials, int n_blocks, int stride, int nscen, int n_mat,
-                    const float* __restrict__ center0, const float* __restrict__ center1, float center_scale,
-                    unsigned long long n_local, double* __restrict__ moments, int out_stride)
-{
-    __shared__ double sh[2][256];
-    const int m = blockIdx.x, rs = blockIdx.y, tid = threadIdx.x;
-    const int run = rs / nscen, s = rs % nscen;
-    const double* p = partials + (size_t)run * n_blocks * stride + (size_t)s * 2 * n_mat + m;
-    double a = 0.0, b = 0.0;
-    for (int blk = tid; blk < n_blocks; blk += 256) {
-        a += p[(size_t)blk * stride];
-        b += p[(size_t)blk * stride + n_mat];
-    }
-    sh[0][tid] = a;
-    sh[1][tid] = b;
-    __syncthreads();
-#pragma unroll
-    for (int o = 128; o > 0; o >>= 1) {
-        if (tid < o) { sh[0][tid] += sh[0][tid + o]; sh[1][tid] += sh[1][tid + o]; }
-        __syncthreads();
-    }
-    if (tid == 0) {
-        double* out = moments + (size_t)run * out_stride + (size_t)s * 2 * n_mat;
-        if (m == 0) { out[0] = 0.0; out[n_mat] = 0.0; }
-        else {
-            const double c = (double)center_scale * (double)(s ? center1 : center0)[m], n = (double)n_local;
-            const double sd = sh[0][0], sdd = sh[1][0];
-            out[m] = sd + n * c;
-            out[n_mat + m] = sdd + 2.0 * c * sd + n * c * c;
-        }
-    }
 }
 
 // =================================================================================================

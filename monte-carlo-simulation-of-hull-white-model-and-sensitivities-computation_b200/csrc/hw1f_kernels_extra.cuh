@@ -318,17 +318,4 @@ fused_kernel(StreamGeom g, SeedArgs seeds, ModelDev md, ScenDev sc, ScenDev scm,
     for (int k = tid; k < nq; k += kThreads) out[k] = bacc[k];
 }
 
-// un-centres the curve part of the fused moment vector in place (see reduce_curve_kernel)
-__global__ void fused_uncenter_kernel(double* __restrict__ moments, int n_mat, const float* __restrict__ center,
-                                      unsigned long long n_local)
-{
-    const int m = threadIdx.x;
-    if (m >= n_mat) return;
-    if (m == 0) { moments[0] = 0.0; moments[n_mat] = 0.0; return; }
-    const double c = (double)center[m], n = (double)n_local;
-    const double sd = moments[m], sdd = moments[n_mat + m];
-    moments[m] = sd + n * c;
-    moments[n_mat + m] = sdd + 2.0 * c * sd + n * c * c;
-}
-
 }  // namespace hw1f
