@@ -93,11 +93,12 @@ int hw1f_default_params(hw1f_params* out);
 /* compute_constants() + compute_drift_tables(): every cudaMemcpyToSymbol of
  * common.cuh:82-83,98-106 and src/3:416-420,428-432,439-441,453-455,518-520. */
 int hw1f_set_model(hw1f_engine* eng, const hw1f_params* p);
-/* Configuration space: n_steps must be a multiple of n_mat - 1 (the reference's #error, common.cuh:25-27).  The curve
- * entry points (hw1f_bond_curve*, hw1f_fused*, hw1f_vega_fd_recalibrated, the recalibration leg of hw1f_vega) walk a
- * whole Box-Muller pair (two steps) at a time and need an EVEN save stride n_steps / (n_mat - 1) and an even normal
- * offset; for an odd stride (e.g. n_steps = 500, n_mat = 101) they return HW1F_ERR_UNSUPPORTED with a message, while
- * hw1f_zbc_cv*, hw1f_vega_pathwise*, hw1f_vega_fd and hw1f_sample_paths take any step count and offset parity. */
+/* Configuration space: n_steps must be a multiple of n_mat - 1 (the reference's #error, common.cuh:25-27); any save
+ * stride n_steps / (n_mat - 1), even or odd, is supported by the curve entry points (hw1f_bond_curve*,
+ * hw1f_vega_fd_recalibrated, hw1f_vega), which need an EVEN normal offset (they start on a Box-Muller pair boundary;
+ * HW1F_ERR_UNSUPPORTED with a message otherwise).  Only the fused single-window pass (hw1f_fused*) needs an even
+ * stride and n_steps_S1 on the maturity grid.  hw1f_zbc_cv*, hw1f_vega_pathwise*, hw1f_vega_fd and hw1f_sample_paths
+ * take any step count and offset parity. */
 int hw1f_get_model(const hw1f_engine* eng, hw1f_params* out);
 /* host copies of the derived constants, for callers that print them */
 typedef struct hw1f_constants {

@@ -592,7 +592,7 @@ size_t smem_fast(const hw1f_engine* e, int ncur)
 size_t smem_curve(const hw1f_engine* e, int nscen)
 {
     const int nq = nscen * 2 * e->p.n_mat;
-    return (size_t)kWinWords * 4 + (size_t)nscen * (e->p.n_steps / 2) * sizeof(float4) + (size_t)nq * sizeof(double) +
+    return (size_t)kWinWords * 4 + (size_t)nscen * ((e->p.n_steps + 1) / 2) * sizeof(float4) + (size_t)nq * sizeof(double) +
            (size_t)kWarps * nq * sizeof(float) + (size_t)nscen * e->p.n_mat * sizeof(float);
 }
 
@@ -715,7 +715,18 @@ int launch_curve(hw1f_engine* e, const Launch& L, const ScenDev* sc, int nscen, 
         const FastTangent tg{0.f, 0.f};
         const size_t smem = smem_fast(e, nscen);
         const ModelDev md = model_dev(e);
-        if (nscen == 1) {
+        if (e->stride & 1) {   // any save stride: the instantiations that may split a Box-Muller pair at a save point
+            HW_REQUIRE(e, dump_steps == 0, "the one-pass recalibration needs an even save stride");
+            if (nscen == 1) {
+                HW_TRY(set_smem(e, (fast_kernel<1, 0, 0, 0, 0, 1>), smem));
+                HW_CUDA(e, launch_k(fast_kernel<1, 0, 0, 0, 0, 1>, grid, kThreads, smem, e->stream, true, L.g, L.seeds, md, c0,
+                                    c1, c0, c0, c0, tg, e->d_plans.p, 0, 0, 0.f, e->d_partials.p, (float2*)nullptr));
+            } else {
+                HW_TRY(set_smem(e, (fast_kernel<2, 0, 0, 0, 0, 1>), smem));
+                HW_CUDA(e, launch_k(fast_kernel<2, 0, 0, 0, 0, 1>, grid, kThreads, smem, e->stream, true, L.g, L.seeds, md, c0,
+                                    c1, c0, c0, c0, tg, e->d_plans.p, 0, 0, 0.f, e->d_partials.p, (float2*)nullptr));
+            }
+        } else if (nscen == 1) {
             HW_TRY(set_smem(e, fast_kernel<1, 0, 0>, smem));
             HW_CUDA(e, launch_k(fast_kernel<1, 0, 0>, grid, kThreads, smem, e->stream, true, L.g, L.seeds, md, c0, c1, c0, c0,
                                 c0, tg, e->d_plans.p, 0, 0, 0.f, e->d_partials.p, (float2*)nullptr));
@@ -733,7 +744,17 @@ int launch_curve(hw1f_engine* e, const Launch& L, const ScenDev* sc, int nscen, 
         return launch_tail(e, L, L.g.n_paths, nq, nscen, c0.emI, c1.emI, 2.0f, d_moments, nq, 0, fin);
     }
     const size_t smem = smem_curve(e, nscen);
-    if (nscen == 1) {
+    if (e->stride & 1) {
+        if (nscen == 1) {
+            HW_TRY(set_smem(e, (bond_curve_kernel<1, 1>), smem));
+            bond_curve_kernel<1, 1><<<grid, kThreads, smem, e->stream>>>(L.g, L.seeds, model_dev(e), sc[0], sc[0],
+                                                                         e->d_partials.p);
+        } else {
+            HW_TRY(set_smem(e, (bond_curve_kernel<2, 1>), smem));
+            bond_curve_kernel<2, 1><<<grid, kThreads, smem, e->stream>>>(L.g, L.seeds, model_dev(e), sc[0], sc[1],
+                                                                         e->d_partials.p);
+        }
+    } else if (nscen == 1) {
         HW_TRY(set_smem(e, bond_curve_kernel<1>, smem));
         bond_curve_kernel<1><<<grid, kThreads, smem, e->stream>>>(L.g, L.seeds, model_dev(e), sc[0], sc[0],
                                                                   e->d_partials.p);
@@ -909,6 +930,10 @@ int init_kernels(hw1f_engine* e)
     HW_CUDA(e, opt_in(fast_kernel<1, 1, 2>, b));
     HW_CUDA(e, opt_in(fast_kernel<1, 3, 2>, b));
     HW_CUDA(e, opt_in((fast_kernel<2, 3, 1, 1, 1>), b));
+    HW_CUDA(e, opt_in((fast_kernel<1, 0, 0, 0, 0, 1>), b));
+    HW_CUDA(e, opt_in((fast_kernel<2, 0, 0, 0, 0, 1>), b));
+    HW_CUDA(e, opt_in((bond_curve_kernel<1, 1>), b));
+    HW_CUDA(e, opt_in((bond_curve_kernel<2, 1>), b));
     HW_CUDA(e, opt_in(zbc_sum_kernel<0>, b));
     HW_CUDA(e, opt_in(zbc_sum_kernel<1>, b));
     HW_CUDA(e, opt_in(zbc_sum_kernel<2>, b));
@@ -1287,8 +1312,8 @@ static int wait_results(hw1f_engine* e)
 
 static int curve_run(hw1f_engine* e, hw1f_rng* rng, double* d_moments, const Finish& fin)
 {
-    if ((rng->offset & 1) || (e->stride & 1)) {
-        e->err = "bond curve needs an even normal offset and an even save stride";
+    if (rng->offset & 1) {
+        e->err = "bond curve needs an even normal offset (it starts on a Box-Muller pair boundary)";
         return HW1F_ERR_UNSUPPORTED;
     }
     Launch L;
@@ -1692,7 +1717,7 @@ static int recal_run(hw1f_engine* e, hw1f_rng* rng, float S1, float S2, float K,
     ScenDev sc[2] = {scen_dev(e, sig_m, host_sig_st(e->p, sig_m), 0), scen_dev(e, sig_p, host_sig_st(e->p, sig_p), 0)};
     Launch L;
     HW_TRY(prepare_launch(e, &rng->seed, 1, rng->first_path, rng->n_paths, rng->offset, &L));
-    const bool one_pass = e->mode == HW1F_MODE_DECOMPOSED && n > 0 && (n % e->stride) == 0 &&
+    const bool one_pass = e->mode == HW1F_MODE_DECOMPOSED && n > 0 && (e->stride & 1) == 0 && (n % e->stride) == 0 &&
                           rng->n_paths <= (1ull << 27);
     Finish fc;
     fc.epi = true;
@@ -1756,8 +1781,8 @@ int hw1f_vega_fd_recalibrated(hw1f_engine* e, hw1f_rng* rng, float S1, float S2,
     if (!rng || !out) return HW1F_ERR_INVALID;
     HW_REQUIRE(e, 2 * rng->n_paths < (1ull << 31), "the reference's int N_total needs 2*n_paths < 2^31");
     HW_CUDA(e, cudaSetDevice(e->device));
-    if ((rng->offset & 1) || (e->stride & 1)) {
-        e->err = "recalibrated FD needs an even normal offset and an even save stride";
+    if (rng->offset & 1) {
+        e->err = "recalibrated FD needs an even normal offset (its curve window starts on a Box-Muller pair boundary)";
         return HW1F_ERR_UNSUPPORTED;
     }
     int32_t n = 0;
@@ -1795,7 +1820,7 @@ int hw1f_vega(hw1f_engine* e, hw1f_rng* rng, float S1, float S2, float K, const 
         HW_TRY(hw1f_vega_fd(e, rng, S1, S2, K, P_mkt, f_mkt, eps, n, out));      // normals [n,2n)
         return hw1f_vega_fd_recalibrated(e, rng, S1, S2, K, eps, n, out);        // normals [2n,..)
     }
-    const bool one_launch = e->mode == HW1F_MODE_DECOMPOSED && n > 0 && (n & 1) == 0 && (n % e->stride) == 0 &&
+    const bool one_launch = e->mode == HW1F_MODE_DECOMPOSED && n > 0 && (n & 1) == 0 && (e->stride & 1) == 0 && (n % e->stride) == 0 &&
                             rng->n_paths <= (1ull << 27) && e->seq_one_launch;
     if (one_launch) {
         // ONE pass over each subsequence's normals (fast_kernel SEQ): pathwise tangent on [off, off+n), both CRN bumps on

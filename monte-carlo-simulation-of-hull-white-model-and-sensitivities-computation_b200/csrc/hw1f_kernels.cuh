@@ -347,7 +347,8 @@ __device__ __forceinline__ void one_pair(ThreadStreams& t, float2& ns, float2& n
 // trees lose nothing: the variance of p0 at short maturities is 1e-10 of its square and would
 // vanish in float32 otherwise.  tail_kernel (hw1f_tail.cuh) undoes the centring in double.
 // Blocks stride over chunks; per-warp float trees -> shared floats -> double block accumulators.
-template <int NSCEN>
+// ODD = 1: any save stride (a save point may fall between the two normals of a Box-Muller pair); separate instantiation
+template <int NSCEN, int ODD = 0>
 __global__ void __launch_bounds__(kThreads, (NSCEN > 1 ? 1 : HW1F_MIN_BLOCKS))
 bond_curve_kernel(StreamGeom g, SeedArgs seeds, ModelDev md, ScenDev sc0, ScenDev sc1, double* __restrict__ partials)
 {
@@ -355,7 +356,7 @@ bond_curve_kernel(StreamGeom g, SeedArgs seeds, ModelDev md, ScenDev sc0, ScenDe
     const int n_steps = md.n_steps, n_mat = md.n_mat;
     const int nq1 = 2 * n_mat;   // per scenario
     const int nq = nq1 * NSCEN;
-    const int n_pairs_tot = n_steps >> 1;
+    const int n_pairs_tot = (n_steps + 1) >> 1;   // an odd step count leaves the last slot half used (tables are zero padded)
     uint32_t* win = smem;
     float4* drift4 = reinterpret_cast<float4*>(smem + kWinWords);                   // [NSCEN][n_steps/2] (d_i,d_i,d_i+1,d_i+1)
     double* bacc = reinterpret_cast<double*>(drift4 + (size_t)NSCEN * n_pairs_tot);  // [nq] block accumulators
@@ -411,9 +412,35 @@ bond_curve_kernel(StreamGeom g, SeedArgs seeds, ModelDev md, ScenDev sc0, ScenDe
             }
         };
 
+        // one step of every scenario with normal G; which = 0 / 1: first / second step of pair pk
+        auto stepfn = [&](int pk, int which, float2 G) {
+#pragma unroll
+            for (int s = 0; s < NSCEN; ++s) {
+                const float4 d = drift4[s * n_pairs_tot + pk];
+                const float2 dd = which ? make_float2(d.z, d.w) : make_float2(d.x, d.y);
+                hw_step2(r1[s], I1[s], fma2(G, sgP[s], dd), e2, hdt2);
+                hw_step2(r2[s], I2[s], fma2(G, sgM[s], dd), e2, hdt2);
+            }
+        };
         int pair = 0;
+        bool pending = false;                  // ODD: the cos half of pair `pair - 1` has not been stepped yet
+        float2 nc_keep = splat(0.0f);
         for (int m = 1; m < n_mat; ++m) {
-            advance_pairs(t, pair, half, pairfn);
+            if (ODD) {
+                int left = md.stride;
+                if (pending) { stepfn(pair - 1, 1, nc_keep); pending = false; --left; }
+                advance_pairs(t, pair, left >> 1, pairfn);
+                if (left & 1) {
+                    float2 ns, nc;
+                    one_pair(t, ns, nc);
+                    stepfn(pair, 0, ns);
+                    ++pair;
+                    nc_keep = nc;
+                    pending = true;
+                }
+            } else {
+                advance_pairs(t, pair, half, pairfn);
+            }
 #pragma unroll
             for (int s = 0; s < NSCEN; ++s) {
                 // p0_m = expf(-integral1) + expf(-integral2)   (market_data.cuh:60)

@@ -113,7 +113,10 @@ __device__ __forceinline__ constexpr int ext_pw() { return NZBC > 0 ? 5 : 0; }
 //         plans[2]) on [n, 2n), then the two recalibration curves (cs0, cs1) on [2n, 2n + n_steps) with the noise state
 //         parked at step n of that window (DUMP) -- one stream derivation instead of three.  Instantiated as
 //         fast_kernel<2, 3, 1, 1, 1>; scenario 0's five ZBC slots stay zero.
-template <int NCUR, int NZBC, int PW, int DUMP = 0, int SEQ = 0>
+// ODD   : 1 = curve sums for ANY save stride (e.g. 500 steps on 101 maturities): a save point may fall between the two
+//         normals of a Box-Muller pair, whose cos half is then carried over to the next interval.  A separate
+//         instantiation (fast_kernel<NCUR, 0, 0, 0, 0, 1>), so the even-stride kernels keep their code.
+template <int NCUR, int NZBC, int PW, int DUMP = 0, int SEQ = 0, int ODD = 0>
 #ifndef HW1F_FAST_MIN_BLOCKS
 #define HW1F_FAST_MIN_BLOCKS 2   // A/B in profiles/r01_ab_variants_decomposed.txt: 512 threads x 2 blocks (64 regs) is best
 #endif
@@ -318,7 +321,23 @@ fast_kernel(StreamGeom g, SeedArgs seeds, ModelDev md, FastScen cs0, FastScen cs
             }
         };
 
-        if (NCUR) {
+        if (NCUR && ODD) {
+            bool pending = false;              // the cos half of the last pair has not been stepped yet
+            float2 nc_keep = splat(0.0f);
+            for (int m = 1; m < n_mat; ++m) {
+                int left = md.stride;
+                if (pending) { step1(nc_keep); pending = false; --left; }
+                advance(left >> 1);
+                if (left & 1) {
+                    float2 ns, nc;
+                    one_pair(t, ns, nc);
+                    step1(ns);
+                    nc_keep = nc;
+                    pending = true;
+                }
+                save_curve(m);
+            }
+        } else if (NCUR) {
             if (SEQ) {   // n_steps_S1 even, normal offset even (checked on the host)
                 advance(n_steps_S1 >> 1);
                 eval_S1(false, true);          // pathwise tangent, normals [0, n)

@@ -382,6 +382,11 @@ def test_grid_stride_chunks_large_run(engine, hw, curve):
     dict(a=0.5, sigma=0.2, r0=0.03, theta_a0=0.02, theta_b0=0.001, theta_a1=0.03, theta_b1=-0.0005, theta_break=4.0),
     # weak mean reversion: 1 - e^{-a dt} = 5e-4, the decomposed kernels' q = qA W - qB h has qA = 4000
     dict(a=0.05, sigma=0.02, r0=0.02),
+    # ODD save strides (the reference's configuration space, common.cuh:25-29): save points fall between the two
+    # normals of a Box-Muller pair
+    dict(n_steps=500, n_mat=101),                                  # stride 5
+    dict(n_steps=700, n_mat=101, T_final=7.0),                     # stride 7
+    dict(n_steps=55, n_mat=12, T_final=5.5),                       # stride 5, ODD step count: the curve ends mid-pair
 ])
 @pytest.mark.parametrize("mode", [0, 1])
 def test_other_model_parameters(hw, over, mode):
@@ -408,6 +413,63 @@ def test_other_model_parameters(hw, over, mode):
         v = eng.vega_pathwise(hw.Rng(6, n), c["P"], c["f"], S1=S1, S2=S2, K=K, n_steps_S1=ns)
         s, _ = o.vega_pathwise_sums(6, n, c["P"], c["f"], S1=S1, S2=S2, K=K, n_steps_S1=ns)
         assert v["vega_pathwise_f64"] == pytest.approx(s / n, rel=2e-5, abs=1e-7)
+    finally:
+        eng.close()
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_odd_save_stride_q3_and_offsets(hw, mode):
+    """stride 5 (500 steps on 101 maturities): hw1f_vega takes the three-call route, the recalibrated FD its second
+    pass, and every estimator equals an engine whose curve inputs come from the oracle-checked path; a curve over an ODD
+    number of steps leaves the handle mid-pair and the next launch picks up the cached cos normal"""
+    from oracle_lib import Oracle
+    over = dict(n_steps=500, n_mat=101)
+    o = Oracle(**over)
+    eng = hw.Engine(device=0, params=hw.default_params(**over))
+    eng.set_mode(mode)
+    try:
+        n = 1 << 12
+        c = eng.bond_curve(hw.Rng(777, n))
+        P, f = o.bond_curve(777, n)
+        assert np.abs(c["P"] / P - 1).max() < 1e-6 and np.abs(c["f"] - f).max() < 5e-6
+        ns = eng.steps_to(5.0)
+        assert ns == 250
+        rng = hw.Rng(778, n)
+        v = eng.vega(rng, c["P"], c["f"], n_steps_S1=ns)
+        assert rng.tell() == 3 * ns
+        pw = eng.vega_pathwise(hw.Rng(778, n), c["P"], c["f"], n_steps_S1=ns)
+        fd = eng.vega_fd(hw.Rng(778, n).seek(ns), c["P"], c["f"], n_steps_S1=ns)
+        rc = eng.vega_fd_recalibrated(hw.Rng(778, n).seek(2 * ns), n_steps_S1=ns)
+        assert v["vega_pathwise"] == pw["vega_pathwise"] and v["vega_fd"] == fd["vega_fd"]
+        assert v["vega_fd_recal"] == rc["vega_fd_recal"]
+        s, _ = o.vega_pathwise_sums(778, n, c["P"], c["f"], n_steps_S1=ns)
+        assert v["vega_pathwise_f64"] == pytest.approx(s / n, rel=2e-5, abs=1e-7)
+        # recalibrated prices against the oracle: curves at sigma -/+ eps on normals [2 ns, 2 ns + 500), prices on [2 ns, 3 ns)
+        eps, sig = np.float32(0.001), np.float32(0.1)
+        prices = []
+        for sg in (sig - eps, sig + eps):
+            sums, _ = o.bond_curve_sums(778, n, offset=2 * ns, sigma=float(sg))     # unshifted base drift
+            Pb, fb = o.curve_finalize(sums, n)
+            mom = o.zbc_moments(778, n, Pb, fb, n_steps_S1=ns, offset=2 * ns, sigma=float(sg))
+            prices.append(o.zbc_algebra(mom, 2 * n, float(Pb[-1]))["price_cv"])
+        assert v["price_minus_recal"] == pytest.approx(prices[0], rel=5e-5)
+        assert v["price_plus_recal"] == pytest.approx(prices[1], rel=5e-5)
+    finally:
+        eng.close()
+    # odd step count: 55 steps -> the handle sits on an odd offset; sample paths continue from the cached cos normal
+    over = dict(n_steps=55, n_mat=12, T_final=5.5)
+    o = Oracle(**over)
+    eng = hw.Engine(device=0, params=hw.default_params(**over))
+    eng.set_mode(mode)
+    try:
+        rng = hw.Rng(779, 64)
+        eng.bond_curve(rng)
+        assert rng.tell() == 55
+        got = eng.sample_paths(rng, 8)
+        want = o.sample_paths(779, 8, offset=55)
+        assert np.abs(got - want).max() < 2e-6
+        with pytest.raises(hw.package.engine.HW1FError):      # a second curve would have to start mid-pair
+            eng.bond_curve(rng)
     finally:
         eng.close()
 
