@@ -342,7 +342,9 @@ int hw1f_debug_normals(hw1f_engine* eng, const hw1f_rng* rng, uint64_t path, int
  * curand_init(seed, path, 2*floor(normal_offset/2)): state6 = {d, v0..v4} */
 int hw1f_host_rng_state(uint64_t seed, uint64_t path, uint64_t normal_offset, uint32_t* state6);
 /* pipe-throughput micro-kernels that give the roofline denominators on this GPU: which =
- * 0 FFMA, 1 FFMA2, 2 MUFU.EX2, 3 SHF/LOP3, 4 I2FP.F32.U32, 5 MUFU+I2FP, 6 HW1F-like mix, 7 FMUL2.
+ * 0 FFMA, 1 FFMA2, 2 MUFU.EX2, 3 SHF/LOP3, 4 I2FP.F32.U32, 5 MUFU+I2FP, 6 HW1F-like mix, 7 FMUL2,
+ * 8 MUFU.LG2, 9 MUFU.SQRT, 10 MUFU.SIN, 11 MUFU.COS, 12 the Box-Muller MUFU mix (LG2, SQRT, SIN, COS in equal parts),
+ * 13 that mix under the other instructions of the decomposed Q1 loop (the count is the MUFU instructions).
  * ms = event time of one launch, thread_instr = probed instructions executed (all threads). */
 int hw1f_pipe_probe(hw1f_engine* eng, int32_t which, int32_t iters, float* ms, double* thread_instr);
 /* number of kernel launches issued by this engine since creation */

@@ -2240,7 +2240,7 @@ int hw1f_host_rng_state(uint64_t seed, uint64_t path, uint64_t normal_offset, ui
 int hw1f_pipe_probe(hw1f_engine* e, int32_t which, int32_t iters, float* ms, double* thread_instr)
 {
     if (!e || !ms || !thread_instr) return HW1F_ERR_INVALID;
-    HW_REQUIRE(e, which >= 0 && which <= 7 && iters >= 1, "which in [0,7], iters >= 1");
+    HW_REQUIRE(e, which >= 0 && which <= 13 && iters >= 1, "which in [0,13], iters >= 1");
     HW_CUDA(e, cudaSetDevice(e->device));
     HW_CUDA(e, e->d_out.ensure(64));
     const int blocks = e->sm_count * 8, threads = 256;
@@ -2254,14 +2254,21 @@ int hw1f_pipe_probe(hw1f_engine* e, int32_t which, int32_t iters, float* ms, dou
             case 4: probe_kernel<4><<<blocks, threads, 0, e->stream>>>(iters, 1.0f, 12345u, e->d_out.p); break;
             case 5: probe_kernel<5><<<blocks, threads, 0, e->stream>>>(iters, 1.0f, 12345u, e->d_out.p); break;
             case 6: probe_kernel<6><<<blocks, threads, 0, e->stream>>>(iters, 1.0f, 12345u, e->d_out.p); break;
-            default: probe_kernel<7><<<blocks, threads, 0, e->stream>>>(iters, 1.0f, 12345u, e->d_out.p); break;
+            case 7: probe_kernel<7><<<blocks, threads, 0, e->stream>>>(iters, 1.0f, 12345u, e->d_out.p); break;
+            case 8: probe_kernel<8><<<blocks, threads, 0, e->stream>>>(iters, 1.0f, 12345u, e->d_out.p); break;
+            case 9: probe_kernel<9><<<blocks, threads, 0, e->stream>>>(iters, 1.0f, 12345u, e->d_out.p); break;
+            case 10: probe_kernel<10><<<blocks, threads, 0, e->stream>>>(iters, 1.0f, 12345u, e->d_out.p); break;
+            case 11: probe_kernel<11><<<blocks, threads, 0, e->stream>>>(iters, 1.0f, 12345u, e->d_out.p); break;
+            case 12: probe_kernel<12><<<blocks, threads, 0, e->stream>>>(iters, 1.0f, 12345u, e->d_out.p); break;
+            default: probe_kernel<13><<<blocks, threads, 0, e->stream>>>(iters, 1.0f, 12345u, e->d_out.p); break;
         }
         HW_TRY(check_launch(e, "probe_kernel"));
         HW_CUDA(e, cudaEventRecord(e->ev1, e->stream));
         HW_CUDA(e, cudaEventSynchronize(e->ev1));
     }
     HW_CUDA(e, cudaEventElapsedTime(ms, e->ev0, e->ev1));
-    // probed instructions per thread (for 4/5: the conversion or the MUFU count; the feeder ops are extra)
+    // probed instructions per thread (for 4/5: the conversion or the MUFU count; the feeder ops are extra;
+    // 10-13: MUFU only -- the other instructions of 13 are the load the MUFU rate is measured under)
     const double per_thread = (which == 6) ? (double)iters * kProbeUnroll * 29.0
                                            : (double)iters * kProbeUnroll * kProbeChains;
     *thread_instr = per_thread * (double)blocks * threads;

@@ -21,6 +21,8 @@ __device__ __forceinline__ float mufu_lg2(float x) { float y; asm("lg2.approx.ft
 __device__ __forceinline__ float mufu_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float mufu_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float mufu_sqrt(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+// sqrt(|x|): the absolute value is an operand modifier of MUFU.SQRT (abs.f32 without .ftz folds; -x under -ftz=true is an FADD)
+__device__ __forceinline__ float mufu_sqrt_abs(float x) { float y; asm("{.reg .f32 t; abs.f32 t, %1; sqrt.approx.ftz.f32 %0, t;}" : "=f"(y) : "f"(x)); return y; }
 // sin/cos.approx expand to FMUL.RZ(x, 1/2pi) + MUFU.SIN/COS, exactly like __sincosf
 __device__ __forceinline__ float mufu_sin(float x) { float y; asm("sin.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float mufu_cos(float x) { float y; asm("cos.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
@@ -84,6 +86,23 @@ __device__ __forceinline__ void box_muller2_parts(uint32_t xa, uint32_t ya, uint
     float2 l = make_float2(mufu_lg2(u.x), mufu_lg2(u.y));
     l = mul2(l, splat(kNeg2Ln2));
     s = make_float2(mufu_sqrt(l.x), mufu_sqrt(l.y));
+    sn = make_float2(mufu_sin(v.x), mufu_sin(v.y));
+    cs = make_float2(mufu_cos(v.x), mufu_cos(v.y));
+}
+
+// the same with the radius left unscaled: s = sqrt(-lg2 u) = sqrt(-2 ln u) / kRadiusScale.  The decomposed kernels carry
+// their (linear) noise recursion in units of kRadiusScale and fold the factor into the constants that read it, which
+// removes the FMUL2 by -2 ln2 from every pair (the negation is an operand modifier of MUFU.SQRT) and one rounding.
+constexpr float kRadiusScale = 1.17741001f;      // sqrt(2 ln 2)
+constexpr float kInvRadiusScale = 0.849321783f;  // 1 / sqrt(2 ln 2)
+__device__ __forceinline__ void box_muller2_parts_raw(uint32_t xa, uint32_t ya, uint32_t xb, uint32_t yb,
+                                                      float2& s, float2& sn, float2& cs)
+{
+    const float2 fx = make_float2(u2f(xa), u2f(xb));
+    const float2 fy = make_float2(u2f(ya), u2f(yb));
+    const float2 u = fma2(fx, splat(__uint_as_float(0x2f800000u)), splat(__uint_as_float(0x2f000000u)));
+    const float2 v = fma2(fy, splat(__uint_as_float(0x30c90fdbu)), splat(__uint_as_float(0x30490fdbu)));
+    s = make_float2(mufu_sqrt_abs(mufu_lg2(u.x)), mufu_sqrt_abs(mufu_lg2(u.y)));   // lg2 u <= 0
     sn = make_float2(mufu_sin(v.x), mufu_sin(v.y));
     cs = make_float2(mufu_cos(v.x), mufu_cos(v.y));
 }

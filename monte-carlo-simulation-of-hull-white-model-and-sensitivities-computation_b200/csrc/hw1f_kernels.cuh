@@ -313,7 +313,7 @@ __device__ __forceinline__ void advance_pairs(ThreadStreams& t, int& pair, int n
 
 // the same walk handing out radius and direction of each pair separately: f(pair_index, s, sin v, cos v)
 // (decomposed kernels fold the products s sin v, s cos v into their fused multiply-adds); j = position in the group
-template <int NP, class PartsFn>
+template <int NP, int RAW = 0, class PartsFn>
 __device__ __forceinline__ void run_pairs_parts(ThreadStreams& t, int pair, PartsFn&& f)
 {
 #pragma unroll
@@ -323,7 +323,8 @@ __device__ __forceinline__ void run_pairs_parts(ThreadStreams& t, int pair, Part
         const uint32_t ya = t.A.next() + (t.dcur + kWeyl * (2 * j + 2));
         const uint32_t yb = t.B.next() + (t.dcurB + kWeyl * (2 * j + 2));
         float2 s, sn, cs;
-        box_muller2_parts(xa, ya, xb, yb, s, sn, cs);
+        if (RAW) box_muller2_parts_raw(xa, ya, xb, yb, s, sn, cs);   // radius in units of kRadiusScale
+        else box_muller2_parts(xa, ya, xb, yb, s, sn, cs);
         f(j, s, sn, cs);
     }
     t.dcur += kWeyl * (2 * NP);

@@ -67,6 +67,14 @@ struct FastTangent {
 #ifndef HW1F_FIXED_HALF
 #define HW1F_FIXED_HALF 1            // 1: a code path for the default save stride (10 steps = one five-pair group)
 #endif
+#ifndef HW1F_FOLD_LN2
+#define HW1F_FOLD_LN2 0              // 1: the noise state is carried in units of sqrt(2 ln2): radius = sqrt(-lg2 u), no FMUL2 by -2 ln2
+                                     // per pair (10 dispatch cycles per loop body less, one rounding less).  Measured: Q1 -0.2 %, but
+                                     // ptxas' schedule of the ZBC / sequence kernels is 2 % slower (profiles/r02_ab_variants.txt, block 3)
+#endif
+#ifndef HW1F_POLY3
+#define HW1F_POLY3 1                 // 1: degree-3 minimax polynomial at the save points (same 2.2e-8 as the degree-4 Taylor form)
+#endif
 
 struct FastState {
     float2 h, W;
@@ -162,7 +170,11 @@ fast_kernel(StreamGeom g, SeedArgs seeds, ModelDev md, FastScen cs0, FastScen cs
     float* const wrow = wflt + warp * nqc + ((lane & 16) ? n_mat : 0);
     // per-scenario exponents: exp(-/+ c q) = ex2(-/+ q * (c log2e))
     const float kc0 = mul_(cs0.c, kLog2e), kc1 = mul_(cs1.c, kLog2e);
-    const float zA0 = mul_(cs0.c, md.qA), zB0 = -mul_(cs0.c, md.qB), zA1 = mul_(cs1.c, md.qA), zB1 = -mul_(cs1.c, md.qB);
+    // HW1F_FOLD_LN2: (h, W) are carried in units of kRadiusScale; every constant that reads them absorbs the factor
+    constexpr int kRaw = HW1F_FOLD_LN2;
+    auto unit_ = [](float x) { return kRaw ? mul_(x, kRadiusScale) : x; };
+    const float zA0 = unit_(mul_(cs0.c, md.qA)), zB0 = -unit_(mul_(cs0.c, md.qB));
+    const float zA1 = unit_(mul_(cs1.c, md.qA)), zB1 = -unit_(mul_(cs1.c, md.qB));
 
     // launched with programmatic stream serialisation behind prep_lo_kernel: everything above overlapped it; the
     // per-launch table U and the bond plans are read only below this point
@@ -178,6 +190,7 @@ fast_kernel(StreamGeom g, SeedArgs seeds, ModelDev md, FastScen cs0, FastScen cs
 
         int pair = 0;
         auto step1 = [&](float2 G) {       // single step (odd lead / tail only)
+            if (kRaw) G = mul2(G, splat(kInvRadiusScale));
             st.W = add2(st.W, G);
             st.h = fma2(st.h, e2, G);
         };
@@ -200,12 +213,12 @@ fast_kernel(StreamGeom g, SeedArgs seeds, ModelDev md, FastScen cs0, FastScen cs
         auto advance = [&](int n_pairs) {
             int k = 0;
             for (; k + 5 <= n_pairs; k += 5) {
-                run_pairs_parts<5>(t, pair, pairfn);
+                run_pairs_parts<5, kRaw>(t, pair, pairfn);
                 pair += 5;
             }
             for (; k < n_pairs; ++k) {
                 st.h = fma2(st.h, splat(md.rho1), st.h);
-                run_pairs_parts<1>(t, pair, pairfn1);
+                run_pairs_parts<1, kRaw>(t, pair, pairfn1);
                 pair += 1;
             }
         };
@@ -246,6 +259,12 @@ fast_kernel(StreamGeom g, SeedArgs seeds, ModelDev md, FastScen cs0, FastScen cs
                     const float2 mid = fma2(w, splat(1.0f / 20160.0f), splat(1.0f / 360.0f));
                     const float2 hi = mul2(w2, splat(1.0f / 1814400.0f));
                     const float2 pl = fma2(w2, add2(mid, hi), lo);
+#elif HW1F_POLY3
+                    // minimax fit of (2 cosh z - 2) / z^2 on w = z^2 in [0, 1.44] with the constant pinned to 1:
+                    // 2.2e-8 relative, the truncation of the degree-4 Taylor form at |z| = 1.2, with one FFMA2 less
+                    float2 pl = fma2(w, splat(5.115120075060986e-05f), splat(0.002776478650048375f));
+                    pl = fma2(pl, w, splat(0.08333364129066467f));
+                    pl = fma2(pl, w, splat(1.0f));
 #else
                     float2 pl = fma2(w, splat(1.0f / 1814400.0f), splat(1.0f / 20160.0f));
                     pl = fma2(pl, w, splat(1.0f / 360.0f));
@@ -256,7 +275,7 @@ fast_kernel(StreamGeom g, SeedArgs seeds, ModelDev md, FastScen cs0, FastScen cs
                 }
                 float2 dv = mul2(d2, splat(emI[s * n_mat + m]));
 #else
-                const float2 y = mul2(st.q(md.qA, md.qB), splat(s ? kc1 : kc0));
+                const float2 y = mul2(st.q(md.qA, md.qB), splat(unit_(s ? kc1 : kc0)));
                 const float2 ep = make_float2(mufu_ex2(y.x), mufu_ex2(y.y));
                 const float2 en = make_float2(mufu_ex2(-y.x), mufu_ex2(-y.y));
                 float2 dv = mul2(add2(add2(ep, en), splat(-2.0f)), splat(emI[s * n_mat + m]));
@@ -268,14 +287,16 @@ fast_kernel(StreamGeom g, SeedArgs seeds, ModelDev md, FastScen cs0, FastScen cs
         };
 
         auto eval_S1 = [&](bool do_zbc, bool do_pw) {
-            const float2 q = st.q(md.qA, md.qB);
+            FastState tu = st;   // the noise state in true units
+            if (kRaw) { tu.h = mul2(st.h, splat(kRadiusScale)); tu.W = mul2(st.W, splat(kRadiusScale)); }
+            const float2 q = tu.q(md.qA, md.qB);
             const double mA = t.validA ? 1.0 : 0.0, mB = t.validB ? 1.0 : 0.0;
 #pragma unroll
             for (int s = (SEQ ? 1 : 0); s < NZBC; ++s) {
                 if (!do_zbc) break;
                 const FastScen z = (s == 0) ? zs0 : (s == 1 ? zs1 : zs2);
                 float2 mom5[5];
-                fast_zbc_mom5(st.h, q, z, plans[s], K, mom5);
+                fast_zbc_mom5(tu.h, q, z, plans[s], K, mom5);
 #pragma unroll
                 for (int k = 0; k < 5; ++k) {
                     const double w = warp_sum((double)mom5[k].x * mA + (double)mom5[k].y * mB);
@@ -285,8 +306,8 @@ fast_kernel(StreamGeom g, SeedArgs seeds, ModelDev md, FastScen cs0, FastScen cs
             if (PW && do_pw) {
                 const BondPlan pl = plans[0];
                 const FastScen z = zs0;
-                const float2 dr = mul2(st.h, splat(z.sg)), dI = mul2(q, splat(z.c));
-                const float2 dt_ = mul2(st.h, splat(pl.c_t));                       // tangent noise
+                const float2 dr = mul2(tu.h, splat(z.sg)), dI = mul2(q, splat(z.c));
+                const float2 dt_ = mul2(tu.h, splat(pl.c_t));                       // tangent noise
                 const float2 dJ = mul2(q, splat(mul_(mul_(0.5f, md.dt), pl.c_t)));   // its integral
                 auto vega_of = [&](float sgn) {
                     const float2 r = fma2(splat(sgn), dr, splat(z.mS1));
@@ -355,7 +376,7 @@ fast_kernel(StreamGeom g, SeedArgs seeds, ModelDev md, FastScen cs0, FastScen cs
 #endif
             for (int m = 1; m < n_mat; ++m) {
 #if HW1F_FIXED_HALF
-                if (half == 5) { run_pairs_parts<5>(t, pair, pairfn); pair += 5; }
+                if (half == 5) { run_pairs_parts<5, kRaw>(t, pair, pairfn); pair += 5; }
                 else advance(half);
 #else
                 advance(half);
@@ -364,9 +385,11 @@ fast_kernel(StreamGeom g, SeedArgs seeds, ModelDev md, FastScen cs0, FastScen cs
                 if (!SEQ && kS1 > 0 && m == m_S1) eval_S1(true, true);
                 if (DUMP && m == m_S1) {
                     float2* d = dump + ((size_t)run * g.n_chunks + chunk) * kChunk + tid;
-                    const float2 q = st.q(md.qA, md.qB);
-                    d[0] = make_float2(st.h.x, q.x);
-                    d[kThreads] = make_float2(st.h.y, q.y);
+                    FastState tu = st;
+                    if (kRaw) { tu.h = mul2(st.h, splat(kRadiusScale)); tu.W = mul2(st.W, splat(kRadiusScale)); }
+                    const float2 q = tu.q(md.qA, md.qB);
+                    d[0] = make_float2(tu.h.x, q.x);
+                    d[kThreads] = make_float2(tu.h.y, q.y);
                 }
             }
         } else {

@@ -10,7 +10,11 @@ constexpr int kProbeUnroll = 64;   // instructions of the probed kind per chain 
 constexpr int kProbeChains = 8;    // independent dependency chains per thread
 
 // which: 0 FFMA, 1 FFMA2, 2 MUFU.EX2, 3 LOP3, 4 I2FP.F32.U32 (+LOP3 feeding it), 5 MUFU.EX2+I2FP mix,
-//        6 FFMA2 + LOP3 + MUFU mix in the HW1F ratio (13:10:4), 7 FMUL2
+//        6 FFMA2 + LOP3 + MUFU mix in the HW1F ratio (13:10:4), 7 FMUL2,
+//        8 MUFU.LG2, 9 MUFU.SQRT, 10 MUFU.SIN (+ its FMUL.RZ), 11 MUFU.COS (+ FMUL.RZ),
+//        12 the Box-Muller MUFU mix LG2 : SQRT : SIN : COS = 1 : 1 : 1 : 1 alone,
+//        13 that mix with the decomposed Q1 loop's other work per four MUFU (14 LOP3/SHF, 4 FFMA2, 2 I2FP; the two FMUL.RZ
+//           come with sin/cos): what a perfectly interleaved instruction stream of the same pipe mix reaches
 template <int WHICH>
 __global__ void __launch_bounds__(256) probe_kernel(int iters, float seedf, uint32_t seedu, float* sink)
 {
@@ -37,6 +41,31 @@ __global__ void __launch_bounds__(256) probe_kernel(int iters, float seedf, uint
                 if (WHICH == 4) { u[c] ^= __float_as_uint(a[c]); a[c] = __uint2float_rn(u[c]); }
                 if (WHICH == 5) { a[c] = mufu_ex2(a[c]); a2[c].x = __uint2float_rn(u[c] ^ __float_as_uint(a2[c].x)); }
                 if (WHICH == 7) a2[c] = mul2(a2[c], m2);
+                if (WHICH == 8) a[c] = mufu_lg2(fabsf(a[c]));
+                if (WHICH == 9) a[c] = mufu_sqrt_abs(a[c]);
+                if (WHICH == 10) a[c] = mufu_sin(a[c]);
+                if (WHICH == 11) a[c] = mufu_cos(a[c]);
+                if (WHICH == 12) {
+                    if ((c & 3) == 0) a[c] = mufu_lg2(fabsf(a[c]));
+                    if ((c & 3) == 1) a[c] = mufu_sqrt_abs(a[c]);
+                    if ((c & 3) == 2) a[c] = mufu_sin(a[c]);
+                    if ((c & 3) == 3) a[c] = mufu_cos(a[c]);
+                }
+            }
+            if (WHICH == 13) {
+#pragma unroll
+                for (int g = 0; g < 2; ++g) {
+                    a[4 * g] = mufu_lg2(fabsf(a[4 * g]));
+                    a[4 * g + 1] = mufu_sqrt_abs(a[4 * g + 1]);
+                    a[4 * g + 2] = mufu_sin(a[4 * g + 2]);
+                    a[4 * g + 3] = mufu_cos(a[4 * g + 3]);
+#pragma unroll
+                    for (int c = 0; c < 14; ++c) u[c & 7] = (u[c & 7] ^ (u[c & 7] << 3)) ^ seedu;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) a2[4 * g + c] = fma2(a2[4 * g + c], m2, b2);
+                    a2[4 * g].x = __uint2float_rn(u[2 * g]);
+                    a2[4 * g + 1].y = __uint2float_rn(u[2 * g + 1]);
+                }
             }
             if (WHICH == 6) {
                 // one "HW1F step pair" worth of pipe pressure: 13 FP2, 10 ALU, 4 MUFU, 2 I2FP
