@@ -45,12 +45,25 @@ constexpr float kNeg2Ln2 = -2.0f * kLn2;             // exact: power-of-two scal
 constexpr uint32_t kWeyl = 362437u;                // curand_kernel.h:872
 
 // ---- XORWOW ---------------------------------------------------------------------------------
+#ifndef HW1F_SHR_IMAD
+#define HW1F_SHR_IMAD 0
+#endif
+#if HW1F_SHR_IMAD
+__constant__ uint32_t kTwo30 = 0x40000000u;
+#endif
 struct Xorwow {
     uint32_t v0, v1, v2, v3, v4;
     // the xorshift half of curand() (curand_kernel.h:866-871); the Weyl half is added by the caller
     __device__ __forceinline__ uint32_t next()
     {
+#if HW1F_SHR_IMAD
+        // v0 >> 2 as the high word of v0 * 2^30: IMAD.HI on the FMA pipe instead of SHF on the (half-rate) ALU pipe, which
+        // the five other integer instructions of a draw already load.  The factor sits in constant memory so that the
+        // compiler cannot turn the multiplication back into a shift.
+        const uint32_t t = v0 ^ __umulhi(v0, kTwo30);
+#else
         const uint32_t t = v0 ^ (v0 >> 2);
+#endif
         v0 = v1; v1 = v2; v2 = v3; v3 = v4;
         v4 = (v4 ^ (v4 << 4)) ^ (t ^ (t << 1));
         return v4;

@@ -90,13 +90,17 @@ def test_reference_zbc(engine, hw, ref):
     n_steps = engine.steps_to(5.0)
     P, f = np.array(ref["P"], np.float32), np.array(ref["f"], np.float32)
     z = engine.zbc_cv(hw.Rng(SEED + 54321, N), P, f, n_steps_S1=n_steps)
-    # measured (profiles/r02_parity_report.json): moments 5.3e-7, price 8.1e-7, beta* 3.6e-6, rho 1.5e-6; two runs of
-    # the reference differ by 3.0e-6 / 2.0e-6 / 5.5e-7 / 9.5e-8
+    # The reference fixture is a LIVE run, and the reference is not deterministic (float atomics): over 16 runs on one
+    # B200 (tools/ref_spread.py -> profiles/r02_ref_spread_16runs.json) its own beta* moves by 2.5e-5, rho by 1.2e-5, the
+    # price by 1.3e-5 relative.  Worst engine-vs-run distance over those 16 runs, both modes: moments 1.0e-6, E[X] 8.1e-7,
+    # price 1.5e-6, beta* 1.02e-5, rho 7.1e-6 (beta* and rho subtract nearly equal moments; medians 3.6e-6 / 2.1e-6).
+    # Bounds = 4x the worst of 16 for the two quotients (a bound of 1e-5 failed one run in ~20), the north-star 1e-5 or
+    # tighter for everything else.
     assert np.allclose(z["mom"], ref["zbc_moments"], rtol=1e-5)
     assert z["mean_X"] == pytest.approx(ref["zbc_mean_X"], rel=1e-5)
     assert z["price_cv"] == pytest.approx(ref["zbc_price_cv"], rel=6e-6)
-    assert z["beta"] == pytest.approx(ref["zbc_beta"], rel=1e-5)
-    assert z["corr"] == pytest.approx(ref["zbc_corr"], rel=1e-5)
+    assert z["beta"] == pytest.approx(ref["zbc_beta"], rel=4e-5)
+    assert z["corr"] == pytest.approx(ref["zbc_corr"], rel=3e-5)
     # ... and far inside the estimators' own standard errors (beta*: 1.2e-3 relative)
     assert abs(z["beta"] - ref["zbc_beta"]) < 0.05 * z["beta_se"]
     assert abs(z["corr"] - ref["zbc_corr"]) < 0.05 * z["corr_se"]
@@ -109,11 +113,12 @@ def test_reference_vega(engine, hw, ref):
     v = engine.vega(hw.Rng(SEED, N), P, f, n_steps_S1=n_steps)
     assert v["vega_pathwise"] == pytest.approx(ref["vega_pathwise"], rel=3e-6)    # measured 4.3e-7
     assert abs(v["vega_pathwise"] - ref["vega_pathwise"]) < 0.01 * v["vega_pathwise_se"]
-    # FD quotients amplify float32 price rounding by 1/(2 eps) = 500.  Measured: vega_fd 2.1e-5 abs (two runs of the
-    # reference: 3.1e-5); vega_fd_recal 3.0e-4 (the reference's recalibrated curves carry its float-atomic error of
-    # ~7e-6 on f(0,5), which the quotient turns into ~3e-4; two runs of the reference: 3.0e-5)
-    assert v["vega_fd"] == pytest.approx(ref["vega_fd"], abs=9e-5)
-    assert v["vega_fd_recal"] == pytest.approx(ref["vega_fd_recal"], abs=9e-4)
+    # FD quotients amplify float32 price rounding by 1/(2 eps) = 500.  Over 16 live runs of the reference
+    # (profiles/r02_ref_spread_16runs.json): its own vega_fd moves by 6.1e-5, its vega_fd_recal by 2.9e-4 (the
+    # recalibrated curves carry its float-atomic error of ~7e-6 on f(0,5), x 500); worst engine-vs-run distance 3.0e-5 /
+    # 5.4e-4.  Bounds = 4x the worst of 16.
+    assert v["vega_fd"] == pytest.approx(ref["vega_fd"], abs=1.2e-4)
+    assert v["vega_fd_recal"] == pytest.approx(ref["vega_fd_recal"], abs=2.2e-3)
 
 
 def test_reference_sample_paths(engine, hw, ref):
