@@ -16,16 +16,33 @@
 
 namespace hw1f {
 
+// Timing ablations (WRONG RESULTS, tools/ablation.sh only): HW1F_ABLATE_MUFU replaces every MUFU of the Box-Muller
+// transform by one FMUL (same dispatch slots, no XU work); HW1F_ABLATE_RNG replaces the xorshift recurrence by one
+// add per draw (the Weyl add, the conversions and the MUFUs stay).  They tell which resource a kernel waits for.
+#ifndef HW1F_ABLATE_MUFU
+#define HW1F_ABLATE_MUFU 0
+#endif
+#ifndef HW1F_ABLATE_RNG
+#define HW1F_ABLATE_RNG 0
+#endif
 // ---- MUFU (XU pipe) wrappers: the approximations --use_fast_math selects ------------------
-__device__ __forceinline__ float mufu_lg2(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float mufu_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float mufu_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+#if HW1F_ABLATE_MUFU
+__device__ __forceinline__ float mufu_lg2(float x) { return __fmul_rn(x, -0.999f); }
+__device__ __forceinline__ float mufu_sqrt(float x) { return __fmul_rn(x, 0.998f); }
+__device__ __forceinline__ float mufu_sqrt_abs(float x) { return __fmul_rn(x, 0.997f); }
+__device__ __forceinline__ float mufu_sin(float x) { return __fmul_rn(x, 0.15f); }
+__device__ __forceinline__ float mufu_cos(float x) { return __fmul_rn(x, 0.14f); }
+#else
+__device__ __forceinline__ float mufu_lg2(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float mufu_sqrt(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 // sqrt(|x|): the absolute value is an operand modifier of MUFU.SQRT (abs.f32 without .ftz folds; -x under -ftz=true is an FADD)
 __device__ __forceinline__ float mufu_sqrt_abs(float x) { float y; asm("{.reg .f32 t; abs.f32 t, %1; sqrt.approx.ftz.f32 %0, t;}" : "=f"(y) : "f"(x)); return y; }
 // sin/cos.approx expand to FMUL.RZ(x, 1/2pi) + MUFU.SIN/COS, exactly like __sincosf
 __device__ __forceinline__ float mufu_sin(float x) { float y; asm("sin.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float mufu_cos(float x) { float y; asm("cos.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+#endif
 
 // ---- scalar FP32 with pinned rounding (never contracted by the compiler) --------------------
 __device__ __forceinline__ float fma_(float a, float b, float c) { return __fmaf_rn(a, b, c); }
@@ -56,6 +73,10 @@ struct Xorwow {
     // the xorshift half of curand() (curand_kernel.h:866-871); the Weyl half is added by the caller
     __device__ __forceinline__ uint32_t next()
     {
+#if HW1F_ABLATE_RNG
+        v4 += v0;          // timing ablation only: one add instead of the six-instruction xorshift step
+        return v4;
+#endif
 #if HW1F_SHR_IMAD
         // v0 >> 2 as the high word of v0 * 2^30: IMAD.HI on the FMA pipe instead of SHF on the (half-rate) ALU pipe, which
         // the five other integer instructions of a draw already load.  The factor sits in constant memory so that the
