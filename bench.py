@@ -108,6 +108,14 @@ class ClockSampler(threading.Thread):
                 "power_w_max": max(s[3] for s in sel), "samples": len(sel)}
 
 
+def read_json(path):
+    try:
+        with open(path) as fh:
+            return json.load(fh)
+    except (OSError, ValueError):
+        return {"file": os.path.relpath(path, ROOT), "missing": True}
+
+
 def read_ncu_capture(rel_path):
     """pipe / issue figures of the dominant kernel from the committed `ncu --set full` summary
     (profiles/*.csv written by tools/ncu_summary.py); nothing is hard-coded here"""
@@ -625,6 +633,7 @@ def main():
         ms, n = eng.pipe_probe(which, iters)
         return n / (ms * 1e-3)
     ffma, ffma2, mufu, alu, i2f, mix = rate(0), rate(1), rate(2), rate(3), rate(4, 128), rate(6, 128)
+    bm_mix = rate(12)                                             # LG2 : SQRT : SIN : COS = 1 : 1 : 1 : 1, the kernel's MUFU mix
     sm_mhz = clocks.get("sm_mhz") or 1965.0
     sm_count = torch.cuda.get_device_properties(local_rank).multi_processor_count
     issue_peak_nominal = sm_count * 4 * 32 * sm_mhz * 1e6        # lane-instructions/s at the clock seen
@@ -656,11 +665,13 @@ def main():
         "fp32_pipe": {"achieved": per_gpu * algo["fp32"] / 1e9, "peak_ffma": ffma / 1e9,
                       "peak_ffma2_lanes": 2 * ffma2 / 1e9, "frac": per_gpu * algo["fp32"] / max(ffma, 2 * ffma2)},
         "probes_Ginstr_s": {"ffma": ffma / 1e9, "ffma2": ffma2 / 1e9, "mufu_ex2": mufu / 1e9, "lop3_shf": alu / 1e9,
-                            "i2fp": i2f / 1e9, "hw1f_mix": mix / 1e9},
+                            "i2fp": i2f / 1e9, "hw1f_mix": mix / 1e9, "mufu_box_muller_mix": bm_mix / 1e9},
         "algorithmic_per_path_step": algo,
         # from the committed ncu --set full summary of this kernel (read from the CSV at run time, not measured in
         # this run): the dispatch port is the co-binding resource -- packed FP32x2 instructions hold it for two cycles
         "ncu_capture": read_ncu_capture(args.ncu_capture or NCU_CAPTURE[args.mode]),
+        # static: committed timing ablations of the decomposed step (not measured in this run)
+        "ablation": read_json(os.path.join(ROOT, "profiles", "r02_ablation.json")) if args.mode == "decomposed" else None,
         "kernel": ("fast_kernel<1,0,0>" if args.mode == "decomposed" else "bond_curve_kernel<1>") +
                   " (prep_lo_kernel + reduce_curve_kernel included in the time)",
         "other_mode": {"mode": other, "ms_per_step": other_ms,
