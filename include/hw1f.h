@@ -98,7 +98,13 @@ int hw1f_set_model(hw1f_engine* eng, const hw1f_params* p);
  * hw1f_vega_fd_recalibrated, hw1f_vega), which need an EVEN normal offset (they start on a Box-Muller pair boundary;
  * HW1F_ERR_UNSUPPORTED with a message otherwise).  Only the fused single-window pass (hw1f_fused*) needs an even
  * stride and n_steps_S1 on the maturity grid.  hw1f_zbc_cv*, hw1f_vega_pathwise*, hw1f_vega_fd and hw1f_sample_paths
- * take any step count and offset parity. */
+ * take any step count and offset parity.
+ * Size limits: n_mat in [3, 1024], n_steps in [2, 8192].  Every single-scenario entry point works over that whole range
+ * (tests/test_gpu_parity.py::test_other_model_parameters runs 2 x 3, 8184 x 1024 and 1023 x 1024 against the oracle); the
+ * two-scenario curve passes (hw1f_vega, hw1f_vega_fd_recalibrated, hw1f_fused*) keep per-warp rows of 2 x 2 x n_mat sums or
+ * both drift tables in shared memory and return HW1F_ERR_UNSUPPORTED ("model too large for shared memory") on the largest
+ * grids (n_mat beyond about 700 in decomposed mode) -- never a wrong result (tools/extreme_configs.py walks every entry point
+ * over the corner configurations in both modes). */
 int hw1f_get_model(const hw1f_engine* eng, hw1f_params* out);
 /* host copies of the derived constants, for callers that print them */
 typedef struct hw1f_constants {

@@ -602,7 +602,7 @@ template <class K>
 int set_smem(hw1f_engine* e, K, size_t bytes)
 {
     if (bytes + 2048 > e->smem_optin) {   // 2 KB head-room for the kernels' static shared arrays
-        e->err = "model too large for shared memory (n_steps * scenarios)";
+        e->err = "model too large for shared memory (n_mat or n_steps x scenarios of this pass; see the size limits in hw1f.h)";
         return HW1F_ERR_UNSUPPORTED;
     }
     return HW1F_OK;
