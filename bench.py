@@ -12,8 +12,9 @@ disjoint subsequence range (weak scaling) and the moment vectors are combined wi
 all-reduce of 202 doubles per step.
 
 `value`  : device-timed (CUDA events on the launching stream), nothing crosses PCIe in the region.
-`e2e`    : the public host-buffer call a user makes (set_model H2D + simulate + finalise + D2H of
-           P, f, P_se), wall-clock between synchronisations.
+`e2e`    : the public host-buffer calls a user makes (set_model H2D + simulate + finalise + D2H of
+           P, f, P_se, every step), wall-clock between synchronisations: hw1f_bond_curve_submit / _collect with two
+           submissions in flight at N = 1 (`e2e.blocking` = the one-call form, the host waiting after every step).
 `roofline`: this path is instruction-issue / FP32+XU pipe bound, not HBM or tensor:
            achieved = algorithmic pipe instructions/s (12 issue slots per path-step), peak = the
            issue rate measured by the engine's own pipe probes on this GPU at the clock seen.
@@ -536,18 +537,47 @@ def main():
     value = path_steps_per_step / (ms_per_step * 1e-3)
 
     # ---- end-to-end region: public host-buffer API, wall clock between synchronisations ----
-    for i in range(3):
-        e2e_step(9000 + i)
-    barrier()
-    t0 = time.time()
-    for i in range(args.steps):
-        last = e2e_step(7000 + i)
-    barrier()
-    e2e_s = torch.tensor([time.time() - t0], dtype=torch.float64, device=dev)
+    def timed_e2e(loop):
+        loop(3, 9000)
+        barrier()
+        t0 = time.time()
+        res = loop(args.steps, 7000)
+        barrier()
+        secs = torch.tensor([time.time() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(secs, op=dist.ReduceOp.MAX)
+        return float(secs.item()) * 1e3 / args.steps, res
+
+    def blocking_loop(n, seed0):
+        res = None
+        for i in range(n):
+            res = e2e_step(seed0 + i)
+        return res
+
+    # the same steps through hw1f_bond_curve_submit / _collect with two submissions in flight: every step still uploads
+    # its model tables (set_model), simulates, and has its P, f, P_se read on the host -- but the GPU starts step i+1
+    # while the host reads step i, so launch latency and the wake-up of the waiting thread do not sit between two
+    # simulations (single GPU; with N > 1 the moments / finish split above is the public path)
+    def submit_collect_loop(n, seed0, depth=2):
+        res, in_flight = None, 0
+        for i in range(n):
+            if in_flight == depth:
+                res = eng.bond_curve_collect(slot=i % depth)
+                in_flight -= 1
+            eng.set_model(eng.params)
+            eng.bond_curve_submit(hw.Rng(seed0 + i, n_paths, first_path=first_path), slot=i % depth)
+            in_flight += 1
+        for i in range(n, n + in_flight):
+            res = eng.bond_curve_collect(slot=i % depth)
+        return res
+
+    e2e_blocking_ms, last = timed_e2e(blocking_loop)
+    e2e_ms, e2e_api = e2e_blocking_ms, "hw1f_bond_curve (blocking)" if world == 1 else "hw1f_bond_curve_moments + all-reduce + hw1f_bond_curve_finish (blocking)"
+    if world == 1:
+        e2e_ms, last_sc = timed_e2e(submit_collect_loop)
+        e2e_api = "hw1f_set_model + hw1f_bond_curve_submit / hw1f_bond_curve_collect, two submissions in flight"
+        assert (last_sc["P"] == last["P"]).all() and (last_sc["f"] == last["f"]).all()   # same seed, same bits
     t_load2 = time.time()
-    if world > 1:
-        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    e2e_ms = float(e2e_s.item()) * 1e3 / args.steps
     e2e_value = path_steps_per_step / (e2e_ms * 1e-3)
     sampler.stop()
     clocks = sampler.summary(t_load0, t_load2)
@@ -730,7 +760,9 @@ def main():
                    "outside the per-step event pairs)", "parallelism": (f"path-range sharding x{world}, one all-reduce of 202 doubles per step "
                                                            f"({collective})") if world > 1 else "single GPU"},
         "collective": {"kind": collective, "check": collective_check},
-        "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms,
+        "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "api": e2e_api,
+                "blocking": {"value": path_steps_per_step / (e2e_blocking_ms * 1e-3), "ms_per_step": e2e_blocking_ms,
+                             "note": "one call at a time: the host waits for every step before it issues the next"},
                 # set_model uploads ONE arena: 2 duplicated drift tables + centring + exp(-Im), 256-byte aligned pieces
                 "h2d_bytes_per_step": 2 * (((n_steps + 2) * 8 + 255) // 256 * 256) + 2 * ((n_mat * 4 + 255) // 256 * 256),
                 "d2h_bytes_per_step": 3 * n_mat * 4},

@@ -142,6 +142,17 @@ int hw1f_rng_prepare(hw1f_engine* eng, const hw1f_rng* rng);
  * P[n_mat], f[n_mat]; P_se[n_mat] (standard error of P from the pair-sample variance; may be
  * NULL); sim_ms (CUDA-event time of the simulation, may be NULL).  Advances rng by n_steps. */
 int hw1f_bond_curve(hw1f_engine* eng, hw1f_rng* rng, float* P, float* f, float* P_se, float* sim_ms);
+/* The same call in two halves, for callers that loop over seeds or models (the reference's drivers do: 20 runs in
+ * src/2:210-468 and src/3:527-654, one curve per bump in src/3:449-482): submit enqueues the model upload already made by
+ * hw1f_set_model, the jump-table launch, the simulation and its tail on the engine's stream and returns at once; the
+ * results land in result slot `slot` (mapped pinned host memory).  collect waits for that slot only and copies P, f
+ * (P_se may be NULL) out.  Up to HW1F_ASYNC_SLOTS submissions may be in flight, so the GPU starts call i+1 while the
+ * host still reads call i -- the launch latency and the wake-up of the waiting thread no longer sit between two
+ * simulations.  Same kernels, same results bit for bit as hw1f_bond_curve.  A slot must be collected before it is
+ * submitted to again; hw1f_set_model with a different n_mat fails while submissions are in flight. */
+#define HW1F_ASYNC_SLOTS 4
+int hw1f_bond_curve_submit(hw1f_engine* eng, hw1f_rng* rng, int32_t slot);
+int hw1f_bond_curve_collect(hw1f_engine* eng, int32_t slot, float* P, float* f, float* P_se);
 /* split form: d_moments[2*n_mat] doubles on the device = {sum_m p0_m, sum_m p0_m^2} over this
  * handle's paths (entry 0 unused).  A caller may all-reduce d_moments across ranks before
  * calling hw1f_bond_curve_finish with the global path count. */

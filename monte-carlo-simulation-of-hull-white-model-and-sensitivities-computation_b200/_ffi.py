@@ -9,6 +9,7 @@ LIB_PATH = os.environ.get("HW1F_LIB") or os.path.join(HERE, "lib", "libhw1f.so")
 
 OK = 0
 MODE_REFERENCE_ORDER, MODE_DECOMPOSED = 0, 1
+ASYNC_SLOTS = 4   # HW1F_ASYNC_SLOTS
 ERR_INVALID, ERR_CUDA, ERR_NO_DEVICE, ERR_UNSUPPORTED, ERR_NO_MODEL, ERR_COMM = 1, 2, 3, 4, 5, 6
 
 
@@ -84,6 +85,8 @@ SYMBOLS = {
     "hw1f_rng_info": (C.c_int, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "hw1f_rng_prepare": (C.c_int, [_P, _P]),
     "hw1f_bond_curve": (C.c_int, [_P, _P, _P, _P, _P, _F]),
+    "hw1f_bond_curve_submit": (C.c_int, [_P, _P, C.c_int32]),
+    "hw1f_bond_curve_collect": (C.c_int, [_P, C.c_int32, _P, _P, _P]),
     "hw1f_bond_curve_moments": (C.c_int, [_P, _P, _P]),
     "hw1f_bond_curve_finish": (C.c_int, [_P, _P, C.c_uint64, _P, _P, _P]),
     "hw1f_bond_curve_ci": (C.c_int, [_P, _P, _P, _P]),

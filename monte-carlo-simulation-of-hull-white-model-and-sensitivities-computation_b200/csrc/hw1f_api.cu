@@ -32,7 +32,9 @@ struct hw1f_rng {
 namespace {
 
 constexpr int kTailCounters = 64;      // ticket counters of the tail kernel: one per run
-constexpr int kResAreas = 4;           // result areas in mapped pinned host memory
+constexpr int kSyncAreas = 4;          // result areas of the blocking entry points (mapped pinned host memory)
+constexpr int kAsyncSlots = HW1F_ASYNC_SLOTS;   // + one area per submit / collect slot
+constexpr int kResAreas = kSyncAreas + kAsyncSlots;
 
 template <class T>
 struct DevBuf {
@@ -67,6 +69,8 @@ struct hw1f_engine {
     size_t smem_optin = 0;
     cudaStream_t stream = nullptr, own_stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr, ev_stage = nullptr;
+    cudaEvent_t ev_slot[HW1F_ASYNC_SLOTS] = {};   // hw1f_bond_curve_submit / _collect: one event per result slot
+    bool slot_busy[HW1F_ASYNC_SLOTS] = {};
     std::string err = "";
     uint64_t launches = 0;
 
@@ -1042,6 +1046,11 @@ int hw1f_engine_create(int device, hw1f_engine** out)
         delete e;
         return HW1F_ERR_CUDA;
     }
+    for (auto& ev : e->ev_slot)
+        if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) {
+            hw1f_engine_destroy(e);
+            return HW1F_ERR_CUDA;
+        }
     e->stream = e->own_stream;
     if (const char* q = std::getenv("HW1F_Q3_ONE_LAUNCH")) e->seq_one_launch = q[0] != '0';
     if (init_kernels(e) != HW1F_OK) {
@@ -1076,6 +1085,7 @@ int hw1f_engine_destroy(hw1f_engine* e)
     if (e->ev2) cudaEventDestroy(e->ev2);
     if (e->ev3) cudaEventDestroy(e->ev3);
     if (e->ev_stage) cudaEventDestroy(e->ev_stage);
+    for (auto ev : e->ev_slot) if (ev) cudaEventDestroy(ev);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
     delete e;
     return HW1F_OK;
@@ -1198,6 +1208,8 @@ int hw1f_set_model(hw1f_engine* e, const hw1f_params* p)
         const size_t nd = (4 * (size_t)nm + 64 > 512) ? 4 * (size_t)nm + 64 : 512, nf = 6 * (size_t)nm;
         const size_t bytes = align(nd * sizeof(double) + nf * sizeof(float));
         if (bytes != e->res_area_bytes) {
+            for (bool busy : e->slot_busy)
+                HW_REQUIRE(e, !busy, "hw1f_set_model: n_mat changes the result areas while submissions are in flight (collect them first)");
             HW_CUDA(e, cudaStreamSynchronize(e->stream));
             if (e->h_res) cudaFreeHost(e->h_res);
             e->h_res = nullptr;
@@ -1388,6 +1400,37 @@ int hw1f_bond_curve(hw1f_engine* e, hw1f_rng* rng, float* P, float* f, float* P_
     HW_TRY(read_curve(e, 0, 0, P, f, P_se));
     if (sim_ms) HW_CUDA(e, cudaEventElapsedTime(sim_ms, e->ev0, e->ev1));
     return HW1F_OK;
+}
+
+// hw1f_bond_curve in two halves: everything is enqueued by submit, collect waits for the slot's event only
+int hw1f_bond_curve_submit(hw1f_engine* e, hw1f_rng* rng, int32_t slot)
+{
+    HW_TRY(require_model(e));
+    if (!rng) return HW1F_ERR_INVALID;
+    HW_REQUIRE(e, slot >= 0 && slot < kAsyncSlots, "slot outside [0, HW1F_ASYNC_SLOTS)");
+    HW_REQUIRE(e, !e->slot_busy[slot], "result slot still in flight: collect it first");
+    HW_CUDA(e, cudaSetDevice(e->device));
+    HW_CUDA(e, e->d_moments.ensure(4 * (size_t)e->p.n_mat * kMaxRuns));
+    HW_TRY(warm_geometry(e, rng));
+    Finish fin;
+    fin.epi = true;
+    fin.n_total = rng->n_paths;
+    fin.host_curve = res_curve(e, kSyncAreas + slot);
+    HW_TRY(curve_run(e, rng, e->d_moments.p, fin));
+    HW_CUDA(e, cudaEventRecord(e->ev_slot[slot], e->stream));
+    e->slot_busy[slot] = true;
+    return HW1F_OK;
+}
+
+int hw1f_bond_curve_collect(hw1f_engine* e, int32_t slot, float* P, float* f, float* P_se)
+{
+    if (!e || !P || !f) return HW1F_ERR_INVALID;
+    HW_REQUIRE(e, slot >= 0 && slot < kAsyncSlots, "slot outside [0, HW1F_ASYNC_SLOTS)");
+    HW_REQUIRE(e, e->slot_busy[slot], "nothing was submitted to this result slot");
+    HW_CUDA(e, cudaSetDevice(e->device));
+    HW_CUDA(e, cudaEventSynchronize(e->ev_slot[slot]));
+    e->slot_busy[slot] = false;
+    return read_curve(e, kSyncAreas + slot, 0, P, f, P_se);
 }
 
 // Standard errors of f(0,T) and theta(T) (and, as a cross-check, of P) by batch means over the simulation blocks of

@@ -187,6 +187,17 @@ class Engine:
                                               C.byref(ms) if timing else None))
         return {"P": P, "f": f, "P_se": se, "sim_ms": ms.value if timing else None}
 
+    def bond_curve_submit(self, rng, slot=0):
+        """hw1f_bond_curve in two halves: enqueue everything now, read the slot later (up to ASYNC_SLOTS in flight)"""
+        self._check(self._lib.hw1f_bond_curve_submit(self._h, rng._h, int(slot)))
+
+    def bond_curve_collect(self, slot=0, with_se=True):
+        P = np.zeros(self.n_mat, np.float32)
+        f = np.zeros(self.n_mat, np.float32)
+        se = np.zeros(self.n_mat, np.float32) if with_se else None
+        self._check(self._lib.hw1f_bond_curve_collect(self._h, int(slot), _ptr(P), _ptr(f), _ptr(se) if with_se else None))
+        return {"P": P, "f": f, "P_se": se}
+
     def bond_curve_moments(self, rng, d_moments_ptr):
         """async: device pointer to 2*n_mat doubles (e.g. a torch.float64 CUDA tensor's data_ptr())."""
         self._check(self._lib.hw1f_bond_curve_moments(self._h, rng._h, C.c_void_p(d_moments_ptr)))

@@ -414,3 +414,35 @@ def test_engine_lifecycle_and_argument_errors(hw, curve):
         e.close()
     h = C.c_void_p()
     assert lib.hw1f_engine_create(99, C.byref(h)) == hw._ffi.ERR_NO_DEVICE
+
+
+def test_bond_curve_submit_collect(engine, hw):
+    """hw1f_bond_curve in two halves: several submissions in flight, collected out of order, bit-identical to the
+    blocking call; slot misuse comes back as a status code"""
+    seeds = [11, 12, 13, 14, 15, 16]
+    want = [engine.bond_curve(hw.Rng(s, 5000 + 37 * s), timing=False) for s in seeds]
+    slots = hw._ffi.ASYNC_SLOTS
+    got = [None] * len(seeds)
+    for k0 in range(0, len(seeds), slots):
+        ks = list(range(k0, min(k0 + slots, len(seeds))))
+        for k in ks:
+            engine.set_model(engine.params)               # the per-call model upload of the reference's drivers
+            engine.bond_curve_submit(hw.Rng(seeds[k], 5000 + 37 * seeds[k]), slot=k - k0)
+        for k in reversed(ks):
+            got[k] = engine.bond_curve_collect(slot=k - k0)
+    for w, g in zip(want, got):
+        for key in ("P", "f", "P_se"):
+            assert (w[key] == g[key]).all(), key
+    # a blocking call between submit and collect does not disturb the slot
+    engine.bond_curve_submit(hw.Rng(seeds[0], 5000 + 37 * seeds[0]), slot=1)
+    other = engine.bond_curve(hw.Rng(99, 4096), timing=False)
+    again = engine.bond_curve_collect(slot=1)
+    assert (again["P"] == want[0]["P"]).all() and not (other["P"][1:] == want[0]["P"][1:]).all()
+    with pytest.raises(hw.HW1FError):
+        engine.bond_curve_collect(slot=2)                 # nothing submitted
+    engine.bond_curve_submit(hw.Rng(1, 2048), slot=0)
+    with pytest.raises(hw.HW1FError):
+        engine.bond_curve_submit(hw.Rng(2, 2048), slot=0)  # still in flight
+    with pytest.raises(hw.HW1FError):
+        engine.bond_curve_submit(hw.Rng(2, 2048), slot=slots)
+    engine.bond_curve_collect(slot=0)
