@@ -83,7 +83,7 @@ struct hw1f_engine {
 
     DevBuf<uint32_t> d_Jpow2;            // [kNumPow][800]
     DevBuf<uint32_t> d_Jnib;             // [4][16][800]: J^(n 16^j), the nibble powers prep_lo_kernel applies
-    DevBuf<uint32_t> d_W;                // window tables
+    DevBuf<uint32_t> d_W;                // window tables of the high jump matrices: [four-bit | five-bit] per matrix
     uint32_t W_hi_base = 0, W_n_hi = 0, W_L_log2 = 0;
     DevBuf<uint32_t> d_U;                // [n_runs][5][L]
     // drift tables, duplicated float2: slot 0 base, 1 sensitivity, 2/3 bumped scenarios
@@ -379,7 +379,7 @@ int ensure_windows(hw1f_engine* e, uint32_t L_log2, uint32_t hi_first, uint32_t 
     if (e->d_W.p && e->W_L_log2 == L_log2 && hi_first >= e->W_hi_base && hi_last < e->W_hi_base + e->W_n_hi)
         return HW1F_OK;
     const uint32_t n_hi = hi_last - hi_first + 1;
-    HW_CUDA(e, e->d_W.ensure((size_t)n_hi * kWinWords));
+    HW_CUDA(e, e->d_W.ensure((size_t)n_hi * kWinStride));
     build_hi_kernel<<<n_hi, 160, 0, e->stream>>>(hi_first, L_log2, e->d_Jpow2.p, e->d_W.p);
     HW_TRY(check_launch(e, "build_hi_kernel"));
     e->W_L_log2 = L_log2;
@@ -586,10 +586,11 @@ FastTangent fast_tangent(const hw1f_engine* e, int n_steps_S1)
 
 int drift_slot_of(const hw1f_engine*, const ScenDev& sc) { return sc.slot; }
 
-size_t smem_fast(const hw1f_engine* e, int ncur)
+// (ncur, nzbc, pw, seq): the template arguments of the fast_kernel instantiation (they pick the window table it stages)
+size_t smem_fast(const hw1f_engine* e, int ncur, int nzbc, int pw, int seq = 0)
 {
     const size_t nqc = (size_t)ncur * 2 * e->p.n_mat;
-    return (size_t)kWinWords * 4 + nqc * sizeof(double) + (size_t)kWarps * nqc * sizeof(float) +
+    return (size_t)fast_win_words(ncur, nzbc, pw, seq) * 4 + nqc * sizeof(double) + (size_t)kWarps * nqc * sizeof(float) +
            (size_t)ncur * e->p.n_mat * sizeof(float) + 64;
 }
 
@@ -717,7 +718,7 @@ int launch_curve(hw1f_engine* e, const Launch& L, const ScenDev* sc, int nscen, 
         const int slot0 = drift_slot_of(e, sc[0]), slot1 = drift_slot_of(e, sc[nscen > 1 ? 1 : 0]);
         const FastScen c0 = fast_scen(e, sc[0].sig_st, slot0, 0), c1 = fast_scen(e, sc[nscen > 1 ? 1 : 0].sig_st, slot1, 0);
         const FastTangent tg{0.f, 0.f};
-        const size_t smem = smem_fast(e, nscen);
+        const size_t smem = smem_fast(e, nscen, 0, 0);
         const ModelDev md = model_dev(e);
         if (e->stride & 1) {   // any save stride: the instantiations that may split a Box-Muller pair at a save point
             HW_REQUIRE(e, dump_steps == 0, "the one-pass recalibration needs an even save stride");
@@ -781,7 +782,7 @@ int launch_zbc(hw1f_engine* e, const Launch& L, const ScenDev* sc, int nscen, in
         const FastScen z0 = fast_scen(e, sc[0].sig_st, drift_slot_of(e, sc[0]), n_steps_S1);
         const FastScen z1 = fast_scen(e, sc[nscen > 1 ? 1 : 0].sig_st, drift_slot_of(e, sc[nscen > 1 ? 1 : 0]), n_steps_S1);
         const FastTangent tg{0.f, 0.f};
-        const size_t smemf = smem_fast(e, 0);
+        const size_t smemf = smem_fast(e, 0, nscen, 0);
         const ModelDev md = model_dev(e);
         if (nscen == 1) {
             HW_TRY(set_smem(e, fast_kernel<0, 1, 0>, smemf));
@@ -832,7 +833,7 @@ int launch_pathwise(hw1f_engine* e, const Launch& L, const ScenDev& sc, int n_st
     if (e->mode == HW1F_MODE_DECOMPOSED) {
         const FastScen z0 = fast_scen(e, sc.sig_st, drift_slot_of(e, sc), n_steps_S1);
         const FastTangent tg = fast_tangent(e, n_steps_S1);
-        const size_t smemf = smem_fast(e, 0);
+        const size_t smemf = smem_fast(e, 0, 0, 1);
         HW_TRY(set_smem(e, fast_kernel<0, 0, 1>, smemf));
         HW_CUDA(e, launch_k(fast_kernel<0, 0, 1>, dim3(L.grid_x, L.n_runs), kThreads, smemf, e->stream, true, L.g, L.seeds,
                             model_dev(e), z0, z0, z0, z0, z0, tg, e->d_plans.p, n_steps_S1, L.lead, K, e->d_partials.p,
@@ -1891,7 +1892,7 @@ int hw1f_vega(hw1f_engine* e, hw1f_rng* rng, float S1, float S2, float K, const 
         const FastScen zb = fast_scen(e, base.sig_st, 0, n), zm = fast_scen(e, three[1].sig_st, 2, n),
                        zp = fast_scen(e, three[2].sig_st, 3, n);
         const FastTangent tg = fast_tangent(e, n);
-        const size_t smem = smem_fast(e, 2);
+        const size_t smem = smem_fast(e, 2, 3, 1, 1);
         HW_TRY(set_smem(e, (fast_kernel<2, 3, 1, 1, 1>), smem));
         HW_CUDA(e, launch_k(fast_kernel<2, 3, 1, 1, 1>, dim3(L.grid_x), kThreads, smem, e->stream, true, L.g, L.seeds,
                             model_dev(e), c0, c1, zb, zm, zp, tg, e->d_plans.p, n, 0, K, e->d_partials.p, e->d_state.p));
@@ -2005,7 +2006,7 @@ static int fused_launch(hw1f_engine* e, hw1f_rng* rng, float S1, float S2, float
         const FastScen c0 = fast_scen(e, sc[0].sig_st, 0, n);
         const FastScen zm = fd ? fast_scen(e, sc[1].sig_st, 2, n) : c0, zp = fd ? fast_scen(e, sc[2].sig_st, 3, n) : c0;
         const FastTangent tg = fast_tangent(e, n);
-        const size_t smemf = smem_fast(e, 1);
+        const size_t smemf = smem_fast(e, 1, 1, 2);
         const ModelDev md = model_dev(e);
         if (fd) {
             HW_TRY(set_smem(e, fast_kernel<1, 3, 2>, smemf));

@@ -202,6 +202,38 @@ __device__ __forceinline__ Xorwow window_matvec(const uint32_t* __restrict__ win
     return s;
 }
 
+// The same product with FIVE-bit windows, the width the decomposed kernels use: 32 windows x 32 values, word k of
+// entry[g][x] = (M * (x << 5g))[k] at win[(k * 32 + g) * 32 + x] (five planes).  The 32 entries of a window are
+// consecutive words of one plane, so a warp's look-up (32 lanes picking among 32 entries) touches distinct banks or
+// broadcasts: ONE shared-memory wavefront per LDS.32 whatever the lanes pick, and the five planes of a look-up sit at
+// compile-time offsets from one address register (SHF + LOP3 + 5 LDS + 2.5 LOP3 per look-up).  The look-ups are the
+// cost of the derivation -- the shared-memory pipe delivers one wavefront per clock and SM, and an LDS.64 / LDS.128
+// whose lanes pick among entries costs 2 / 5 wavefronts (tools/probes/lds_probe.cu) -- so the window is as wide as a
+// wavefront allows: 32 look-ups x 5 words per stream instead of 40 x 5.  A wider window would put two entries on one
+// bank and pay every look-up twice.
+constexpr int kWin5Groups = 32, kWin5Entries = 32, kWin5Plane = kWin5Groups * kWin5Entries;
+constexpr int kWin5Words = 5 * kWin5Plane;   // 5120 uint32 = 20480 B
+// global layout: the two tables of one matrix sit side by side, [four-bit table | five-bit table] per matrix
+constexpr int kWinStride = kWinWords + kWin5Words;
+
+__device__ __forceinline__ Xorwow window5_matvec(const uint32_t* __restrict__ win, const uint32_t u[5])
+{
+    uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0;
+#pragma unroll
+    for (int g = 0; g < kWin5Groups; ++g) {
+        const int b = 5 * g, w = b >> 5, sh = b & 31;   // compile-time after unrolling
+        uint32_t x;
+        if (sh + 5 <= 32) x = u[w] >> sh;
+        else x = __funnelshift_r(u[w], u[w + 1 < 5 ? w + 1 : 4], sh);   // a window across two state words (never the last)
+        x &= 31u;
+        const uint32_t* e = win + g * kWin5Entries + x;
+        a0 ^= e[0]; a1 ^= e[kWin5Plane]; a2 ^= e[2 * kWin5Plane]; a3 ^= e[3 * kWin5Plane]; a4 ^= e[4 * kWin5Plane];
+    }
+    Xorwow s;
+    s.v0 = a0; s.v1 = a1; s.v2 = a2; s.v3 = a3; s.v4 = a4;
+    return s;
+}
+
 // one warp multiplies a 160-bit vector (replicated in every lane) by a row-image matrix in
 // global memory: lane l owns bits l, l+32, .. of the input
 __device__ __forceinline__ void warp_matvec(const uint32_t* __restrict__ mat, uint32_t v[5], int lane)

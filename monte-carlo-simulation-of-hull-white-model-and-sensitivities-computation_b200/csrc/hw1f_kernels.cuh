@@ -41,7 +41,8 @@ struct SeedBlock {
 struct SeedArgs { SeedBlock s[kMaxRuns]; };
 
 struct StreamGeom {
-    const uint32_t* W;     // [n_hi][kWinWords] window tables of J^((hi_base+h)*L)
+    const uint32_t* W;     // [n_hi][kWinStride] window tables of J^((hi_base+h)*L): four-bit windows (kWinWords), then the
+                           // same matrix with five-bit windows (kWin5Words)
     const uint32_t* U;     // [n_runs][5][L]   lo vectors, SoA per run
     unsigned long long first_path, n_paths;
     unsigned long long chunk0;  // first_path / kChunk
@@ -221,7 +222,7 @@ build_hi_kernel(uint32_t hi_base, uint32_t L_log2, const uint32_t* __restrict__ 
         __syncthreads();
         cur ^= 1;
     }
-    uint32_t* out = W + (size_t)blockIdx.x * kWinWords;
+    uint32_t* out = W + (size_t)blockIdx.x * kWinStride;
     for (int e = r; e < kWinGroups * 16; e += 160) {
         const int g = e >> 4, x = e & 15;
         uint32_t a[5] = {0, 0, 0, 0, 0};
@@ -234,6 +235,20 @@ build_hi_kernel(uint32_t hi_base, uint32_t L_log2, const uint32_t* __restrict__ 
 #pragma unroll
         for (int k = 0; k < 5; ++k) out[e * 5 + k] = a[k];
     }
+    // the same matrix as a five-bit window table (layout: window5_matvec, hw1f_device.cuh)
+    uint32_t* out5 = out + kWinWords;
+    for (int e = r; e < kWin5Plane; e += 160) {
+        const int g = e >> 5, x = e & 31;
+        uint32_t a[5] = {0, 0, 0, 0, 0};
+#pragma unroll
+        for (int b = 0; b < 5; ++b)
+            if ((x >> b) & 1) {
+#pragma unroll
+                for (int k = 0; k < 5; ++k) a[k] ^= M[cur][5 * g + b][k];
+            }
+#pragma unroll
+        for (int k = 0; k < 5; ++k) out5[k * kWin5Plane + e] = a[k];
+    }
 }
 
 // =================================================================================================
@@ -245,17 +260,20 @@ struct ThreadStreams {
     uint32_t dcur, dcurB;
 };
 
+// WB = window width of the table staged in `win`: 4 (kWinWords words, reference-order kernels) or 5 (kWin5Words)
+template <int WB = 4>
 __device__ __forceinline__ ThreadStreams derive_streams(const StreamGeom& g, const SeedArgs& seeds, int run,
                                                          unsigned long long chunk,
-                                                         uint32_t* win /* smem, kWinWords */)
+                                                         uint32_t* win /* smem, kWinWords or kWin5Words */)
 {
+    constexpr int kWords = (WB == 5) ? kWin5Words : kWinWords;
     const int tid = threadIdx.x;
     const unsigned long long base = (g.chunk0 + chunk) << kChunkLog2;
     __syncthreads();   // every warp is done with the previous chunk's window table
     const uint32_t L = 1u << g.L_log2;
     const uint32_t hi = (uint32_t)(base >> g.L_log2) - g.hi_base;
-    const uint4* wsrc = reinterpret_cast<const uint4*>(g.W + (size_t)hi * kWinWords);
-    for (int i = tid; i < kWinWords / 4; i += kThreads) reinterpret_cast<uint4*>(win)[i] = wsrc[i];
+    const uint4* wsrc = reinterpret_cast<const uint4*>(g.W + (size_t)hi * kWinStride + (WB == 5 ? kWinWords : 0));
+    for (int i = tid; i < kWords / 4; i += kThreads) reinterpret_cast<uint4*>(win)[i] = wsrc[i];
     const uint32_t loA = (uint32_t)(base & (L - 1)) + tid;
     const uint32_t loB = loA + kThreads;
     const uint32_t* Urun = g.U + (size_t)run * 5 * L;
@@ -267,8 +285,8 @@ __device__ __forceinline__ ThreadStreams derive_streams(const StreamGeom& g, con
     }
     __syncthreads();
     ThreadStreams t;
-    t.A = window_matvec(win, uA);
-    t.B = window_matvec(win, uB);
+    t.A = (WB == 5) ? window5_matvec(win, uA) : window_matvec(win, uA);
+    t.B = (WB == 5) ? window5_matvec(win, uB) : window_matvec(win, uB);
     const unsigned long long pA = base + tid, pB = pA + kThreads;
     t.validA = (pA >= g.first_path) && (pA < g.first_path + g.n_paths);
     t.validB = (pB >= g.first_path) && (pB < g.first_path + g.n_paths);
@@ -783,7 +801,7 @@ __global__ void sample_paths_kernel(StreamGeom g, SeedArgs seeds, ModelDev md, S
     uint32_t u[5];
 #pragma unroll
     for (int w = 0; w < 5; ++w) u[w] = g.U[(size_t)w * L + lo];
-    Xorwow st = window_matvec(g.W + (size_t)hi * kWinWords, u);
+    Xorwow st = window_matvec(g.W + (size_t)hi * kWinStride, u);
     uint32_t d = seeds.s[0].d_start;
     if (dbg_state) {
         uint32_t* o = dbg_state + (size_t)q * 6;

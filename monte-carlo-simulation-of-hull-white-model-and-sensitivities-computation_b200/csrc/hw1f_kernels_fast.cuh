@@ -76,6 +76,37 @@ struct FastTangent {
 #define HW1F_POLY3 1                 // 1: degree-3 minimax polynomial at the save points (same 2.2e-8 as the degree-4 Taylor form)
 #endif
 
+// Window width of the stream derivation per instantiation (hw1f_device.cuh: window5_matvec).  The five-bit table
+// saves a fifth of the look-ups (prologue 1289 -> 1079 instructions, 400 -> 320 LDS; 2-step ZBC call 48.1 -> 44.7 us),
+// but the width also changes how ptxas orders the time loops behind the prologue, which is worth +-1 % on its own
+// (DESIGN.md section 4): the width is therefore chosen per kernel family BY MEASUREMENT
+// (profiles/r02_ab_window_width.txt): curve, ZBC and fused kernels five bits (Q1 -0.4 %, ZBC -0.6 %, 20-seed batch
+// -0.7 %, recalibration curves -0.35 %, fused -0.65 %), pathwise and the one-launch Q3 sequence four (five bits: 0 % and
+// +1.9 % -- the sequence kernel's three loops come out in a slower order behind the shorter prologue).
+#ifndef HW1F_WIN_BITS_CURVE
+#define HW1F_WIN_BITS_CURVE 5
+#endif
+#ifndef HW1F_WIN_BITS_ZBC
+#define HW1F_WIN_BITS_ZBC 5
+#endif
+#ifndef HW1F_WIN_BITS_FUSED
+#define HW1F_WIN_BITS_FUSED 5
+#endif
+#ifndef HW1F_WIN_BITS_OTHER
+#define HW1F_WIN_BITS_OTHER 4
+#endif
+__host__ __device__ constexpr int fast_win_bits(int ncur, int nzbc, int pw, int seq)
+{
+    return (ncur > 0 && nzbc == 0 && pw == 0 && !seq) ? HW1F_WIN_BITS_CURVE
+         : (ncur == 0 && nzbc > 0 && pw == 0)          ? HW1F_WIN_BITS_ZBC
+         : (ncur > 0 && nzbc > 0 && !seq)              ? HW1F_WIN_BITS_FUSED
+                                                       : HW1F_WIN_BITS_OTHER;
+}
+__host__ __device__ constexpr int fast_win_words(int ncur, int nzbc, int pw, int seq)
+{
+    return fast_win_bits(ncur, nzbc, pw, seq) == 5 ? kWin5Words : kWinWords;
+}
+
 struct FastState {
     float2 h, W;
     __device__ __forceinline__ float2 q(float qA, float qB) const { return fma2(W, splat(qA), mul2(h, splat(-qB))); }
@@ -142,7 +173,8 @@ fast_kernel(StreamGeom g, SeedArgs seeds, ModelDev md, FastScen cs0, FastScen cs
     const int nqc = NCUR * 2 * n_mat;
     const int nq = nqc + kS1;
     uint32_t* win = smem;
-    double* bacc = reinterpret_cast<double*>(smem + kWinWords);                  // [nqc]
+    constexpr int WB = fast_win_bits(NCUR, NZBC, PW, SEQ);
+    double* bacc = reinterpret_cast<double*>(smem + fast_win_words(NCUR, NZBC, PW, SEQ));   // [nqc]
     float* wflt = reinterpret_cast<float*>(bacc + (NCUR ? nqc : 0));            // [kWarps][nqc]
     float* emI = wflt + (NCUR ? kWarps * nqc : 0);                              // [NCUR][n_mat]
     __shared__ double wext[kWarps][kS1 > 0 ? kS1 : 1];
@@ -181,7 +213,7 @@ fast_kernel(StreamGeom g, SeedArgs seeds, ModelDev md, FastScen cs0, FastScen cs
     asm volatile("griddepcontrol.wait;" ::: "memory");
 
     for (unsigned long long chunk = blockIdx.x; chunk < g.n_chunks; chunk += gridDim.x) {
-        ThreadStreams t = derive_streams(g, seeds, run, chunk, win);
+        ThreadStreams t = derive_streams<WB>(g, seeds, run, chunk, win);
         FastState st;
         st.h = splat(0.0f);
         st.W = splat(0.0f);

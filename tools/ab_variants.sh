@@ -14,9 +14,16 @@ N = 1 << 20
 eng = hw.Engine(device=0)
 c = eng.bond_curve(hw.Rng(1234, N)); P, f = c["P"], c["f"]
 z = sorted(eng.zbc_cv(hw.Rng(i, N), P, f, n_steps_S1=500)["sim_ms"] for i in range(25))[5:-5]
-for i in range(3): eng.vega(hw.Rng(i, N), P, f, n_steps_S1=500)
-t0 = time.perf_counter()
-for i in range(20): eng.vega(hw.Rng(50 + i, N), P, f, n_steps_S1=500)
-print("    zbc event ms %.4f   q3 sequence wall ms %.4f" % (sum(z) / len(z), (time.perf_counter() - t0) * 1e3 / 20))
+def wall(fn, n=20):
+    for i in range(3): fn(i)
+    t0 = time.perf_counter()
+    for i in range(n): fn(50 + i)
+    return (time.perf_counter() - t0) * 1e3 / n
+q3 = wall(lambda i: eng.vega(hw.Rng(i, N), P, f, n_steps_S1=500))
+pw = wall(lambda i: eng.vega_pathwise(hw.Rng(i, N), P, f, n_steps_S1=500))
+fu = wall(lambda i: eng.fused(hw.Rng(i, N), P, f, n_steps_S1=500))
+rc = wall(lambda i: eng.vega_fd_recalibrated(hw.Rng(i, N), n_steps_S1=500))
+zb = wall(lambda i: eng.zbc_cv_batch(list(range(i, i + 20)), N, P, f, n_steps_S1=500), 5)
+print("    zbc event ms %.4f   q3 sequence wall ms %.4f   pathwise %.4f   fused %.4f   recal FD %.4f   zbc x20 %.3f" % (sum(z) / len(z), q3, pw, fu, rc, zb))
 PY
 done
