@@ -354,7 +354,8 @@ uint32_t pick_L_log2(uint64_t n_paths)
 {
     uint32_t lg = 0;
     while ((1ull << lg) < n_paths) ++lg;
-    uint32_t L = lg / 2 + 1;
+    static const int bias = std::getenv("HW1F_L_BIAS") ? std::atoi(std::getenv("HW1F_L_BIAS")) : 0;   // A/B only
+    uint32_t L = lg / 2 + 1 + bias;
     if (L < (uint32_t)kChunkLog2) L = kChunkLog2;
     if (L > 16) L = 16;
     return L;

@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """Do two builds of libhw1f.so schedule their time loops the same way?  For every simulation kernel the opcode sequence
-from the first Box-Muller MUFU.LG2 to the end of the kernel is compared between the two libraries: "loops identical"
+from the first to the last Box-Muller MUFU.LG2 (the time loops and what lies between them) is compared between the two libraries: "loops identical"
 means a source change stayed in the prologue and the measured difference is not ptxas' instruction order (which is worth
 +-2 % on these kernels).  Needs only cuobjdump (no GPU).
 
@@ -37,7 +37,7 @@ def main(old, new):
         ib = [i for i, op in enumerate(b[name]) if op.startswith("MUFU.LG2")]
         if not ia or not ib:
             continue
-        ta, tb = a[name][ia[0]:], b[name][ib[0]:]
+        ta, tb = a[name][ia[0]:ia[-1] + 1], b[name][ib[0]:ib[-1] + 1]
         verdict = "loops identical" if ta == tb else \
             "loops differ (similarity %.3f)" % difflib.SequenceMatcher(None, ta, tb, autojunk=False).ratio()
         short = subprocess.run(["c++filt", name], capture_output=True, text=True).stdout.split("(")[0].strip()
