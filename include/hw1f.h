@@ -143,13 +143,18 @@ int hw1f_rng_prepare(hw1f_engine* eng, const hw1f_rng* rng);
  * NULL); sim_ms (CUDA-event time of the simulation, may be NULL).  Advances rng by n_steps. */
 int hw1f_bond_curve(hw1f_engine* eng, hw1f_rng* rng, float* P, float* f, float* P_se, float* sim_ms);
 /* The same call in two halves, for callers that loop over seeds or models (the reference's drivers do: 20 runs in
- * src/2:210-468 and src/3:527-654, one curve per bump in src/3:449-482): submit enqueues the model upload already made by
- * hw1f_set_model, the jump-table launch, the simulation and its tail on the engine's stream and returns at once; the
- * results land in result slot `slot` (mapped pinned host memory).  collect waits for that slot only and copies P, f
- * (P_se may be NULL) out.  Up to HW1F_ASYNC_SLOTS submissions may be in flight, so the GPU starts call i+1 while the
- * host still reads call i -- the launch latency and the wake-up of the waiting thread no longer sit between two
- * simulations.  Same kernels, same results bit for bit as hw1f_bond_curve.  A slot must be collected before it is
- * submitted to again; hw1f_set_model with a different n_mat fails while submissions are in flight. */
+ * src/2:210-468 and src/3:527-654, one curve per bump in src/3:449-482): submit enqueues the jump-table launch, the
+ * simulation and its tail and returns at once; the results land in result slot `slot` (mapped pinned host memory).
+ * collect waits for that slot only and copies P, f (P_se may be NULL) out.  Up to HW1F_ASYNC_SLOTS submissions may be in
+ * flight.  Every slot is a lane of its own: slot 0 runs on the engine's stream, slot k > 0 on an internal twin of the
+ * engine (own stream, scratch and tables, created by the first submission to that slot; it follows every
+ * hw1f_set_model / hw1f_engine_set_mode of the caller).  Walk the slots round robin and the GPU works on the next calls
+ * -- jump tables, stream derivation of the first wave -- under the drain and the tail of the current one, while the host
+ * reads the previous one.  Measured at 2^20 subsequences (tools/two_engine_probe.py): 0.600 ms per call blocking,
+ * 0.580 with two submissions in one lane, 0.564 with two lanes, 0.553 with four.  Same kernels, same results bit for bit
+ * as hw1f_bond_curve.  A slot must be collected before it is submitted to again; calls in different slots are not
+ * ordered against each other; hw1f_engine_set_stream moves slot 0 only; hw1f_set_model with a different n_mat fails
+ * while submissions are in flight; hw1f_bond_curve_ci sees slot-0 launches only. */
 #define HW1F_ASYNC_SLOTS 4
 int hw1f_bond_curve_submit(hw1f_engine* eng, hw1f_rng* rng, int32_t slot);
 int hw1f_bond_curve_collect(hw1f_engine* eng, int32_t slot, float* P, float* f, float* P_se);

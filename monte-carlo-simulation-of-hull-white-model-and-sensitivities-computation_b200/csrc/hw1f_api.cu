@@ -71,6 +71,12 @@ struct hw1f_engine {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr, ev_stage = nullptr;
     cudaEvent_t ev_slot[HW1F_ASYNC_SLOTS] = {};   // hw1f_bond_curve_submit / _collect: one event per result slot
     bool slot_busy[HW1F_ASYNC_SLOTS] = {};
+    // Every result slot is a lane of its own: slot 0 runs on this engine, slot k > 0 on a twin engine (own stream, scratch
+    // and jump tables, created by the first submission to that slot, same model and mode), so that submissions in flight
+    // overlap on the GPU -- the jump-table launch and the first wave's stream derivation of one call run under the drain
+    // and the tail of another
+    hw1f_engine* twin[HW1F_ASYNC_SLOTS] = {};   // [0] unused
+    uint64_t model_gen = 0, twin_gen[HW1F_ASYNC_SLOTS] = {};   // hw1f_set_model calls seen by this engine / forwarded to a twin
     std::string err = "";
     uint64_t launches = 0;
 
@@ -1067,6 +1073,10 @@ int hw1f_engine_create(int device, hw1f_engine** out)
 int hw1f_engine_destroy(hw1f_engine* e)
 {
     if (!e) return HW1F_OK;
+    for (auto& t : e->twin) {
+        if (t) hw1f_engine_destroy(t);
+        t = nullptr;
+    }
     cudaSetDevice(e->device);
     cudaStreamSynchronize(e->stream);
     e->d_Jpow2.release(); e->d_Jnib.release(); e->d_W.release(); e->d_U.release();
@@ -1129,6 +1139,7 @@ int hw1f_engine_synchronize(hw1f_engine* e)
     if (!e) return HW1F_ERR_INVALID;
     HW_CUDA(e, cudaSetDevice(e->device));
     HW_CUDA(e, cudaStreamSynchronize(e->stream));
+    for (auto t : e->twin) if (t) HW_CUDA(e, cudaStreamSynchronize(t->stream));
     return HW1F_OK;
 }
 
@@ -1222,6 +1233,7 @@ int hw1f_set_model(hw1f_engine* e, const hw1f_params* p)
         }
     }
     e->has_model = true;
+    ++e->model_gen;
     // compute_constants(): ONE host->device copy of the model tables (every call, like the reference's
     // cudaMemcpyToSymbol sequence; only the host-side table building is cached)
     HW_CUDA(e, cudaMemcpyAsync(e->d_model.p, e->h_model, total, cudaMemcpyHostToDevice, e->stream));
@@ -1404,7 +1416,28 @@ int hw1f_bond_curve(hw1f_engine* e, hw1f_rng* rng, float* P, float* f, float* P_
     return HW1F_OK;
 }
 
-// hw1f_bond_curve in two halves: everything is enqueued by submit, collect waits for the slot's event only
+// hw1f_bond_curve in two halves: everything is enqueued by submit, collect waits for the slot's event only.  Slot 0
+// runs on this engine's stream, the other slots on their twins': lanes whose kernels the GPU overlaps.
+static int lane_of(hw1f_engine* e, int32_t slot, hw1f_engine** lane)
+{
+    *lane = e;
+    if (slot == 0) return HW1F_OK;
+    if (!e->twin[slot]) {
+        const int st = hw1f_engine_create(e->device, &e->twin[slot]);
+        if (st != HW1F_OK) { e->err = "could not create a submission lane"; return st; }
+        e->twin_gen[slot] = 0;
+    }
+    hw1f_engine* t = e->twin[slot];
+    t->mode = e->mode;
+    if (e->twin_gen[slot] != e->model_gen) {   // every hw1f_set_model of the caller reaches the lane that runs the next call
+        const int st = hw1f_set_model(t, &e->p);
+        if (st != HW1F_OK) { e->err = t->err; return st; }
+        e->twin_gen[slot] = e->model_gen;
+    }
+    *lane = t;
+    return HW1F_OK;
+}
+
 int hw1f_bond_curve_submit(hw1f_engine* e, hw1f_rng* rng, int32_t slot)
 {
     HW_TRY(require_model(e));
@@ -1412,14 +1445,26 @@ int hw1f_bond_curve_submit(hw1f_engine* e, hw1f_rng* rng, int32_t slot)
     HW_REQUIRE(e, slot >= 0 && slot < kAsyncSlots, "slot outside [0, HW1F_ASYNC_SLOTS)");
     HW_REQUIRE(e, !e->slot_busy[slot], "result slot still in flight: collect it first");
     HW_CUDA(e, cudaSetDevice(e->device));
-    HW_CUDA(e, e->d_moments.ensure(4 * (size_t)e->p.n_mat * kMaxRuns));
-    HW_TRY(warm_geometry(e, rng));
-    Finish fin;
-    fin.epi = true;
-    fin.n_total = rng->n_paths;
-    fin.host_curve = res_curve(e, kSyncAreas + slot);
-    HW_TRY(curve_run(e, rng, e->d_moments.p, fin));
-    HW_CUDA(e, cudaEventRecord(e->ev_slot[slot], e->stream));
+    hw1f_engine* t = nullptr;
+    HW_TRY(lane_of(e, slot, &t));
+    int st = HW1F_OK;
+    auto run = [&]() -> int {
+        HW_CUDA(t, t->d_moments.ensure(4 * (size_t)t->p.n_mat * kMaxRuns));
+        HW_TRY(warm_geometry(t, rng));
+        Finish fin;
+        fin.epi = true;
+        fin.n_total = rng->n_paths;
+        fin.host_curve = res_curve(t, kSyncAreas + slot);
+        HW_TRY(curve_run(t, rng, t->d_moments.p, fin));
+        HW_CUDA(t, cudaEventRecord(t->ev_slot[slot], t->stream));
+        return HW1F_OK;
+    };
+    st = run();
+    if (st != HW1F_OK) {
+        if (t != e) e->err = t->err;
+        return st;
+    }
+    if (t != e) e->ci_valid = false;   // the block partials of this launch live in the other lane
     e->slot_busy[slot] = true;
     return HW1F_OK;
 }
@@ -1430,9 +1475,12 @@ int hw1f_bond_curve_collect(hw1f_engine* e, int32_t slot, float* P, float* f, fl
     HW_REQUIRE(e, slot >= 0 && slot < kAsyncSlots, "slot outside [0, HW1F_ASYNC_SLOTS)");
     HW_REQUIRE(e, e->slot_busy[slot], "nothing was submitted to this result slot");
     HW_CUDA(e, cudaSetDevice(e->device));
-    HW_CUDA(e, cudaEventSynchronize(e->ev_slot[slot]));
+    hw1f_engine* t = slot ? e->twin[slot] : e;
+    HW_CUDA(e, cudaEventSynchronize(t->ev_slot[slot]));
     e->slot_busy[slot] = false;
-    return read_curve(e, kSyncAreas + slot, 0, P, f, P_se);
+    const int st = read_curve(t, kSyncAreas + slot, 0, P, f, P_se);
+    if (st != HW1F_OK && t != e) e->err = t->err;
+    return st;
 }
 
 // Standard errors of f(0,T) and theta(T) (and, as a cross-check, of P) by batch means over the simulation blocks of
@@ -2341,6 +2389,7 @@ int hw1f_launch_count(const hw1f_engine* e, uint64_t* n)
 {
     if (!e || !n) return HW1F_ERR_INVALID;
     *n = e->launches;
+    for (auto t : e->twin) if (t) *n += t->launches;
     return HW1F_OK;
 }
 
