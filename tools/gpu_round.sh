@@ -11,6 +11,7 @@ echo "== bench reference" ; python bench.py --impl reference --steps 20 --warmup
 echo "== bench" ; python bench.py 2> $OUT/${TAG}_bench.err | tee $OUT/${TAG}_bench.json | cut -c1-400
 echo "== api overhead" ; python tools/api_overhead.py > $OUT/${TAG}_api_overhead.json 2>&1
 echo "== fixed cost" ; python tools/fixed_cost_probe.py 2>&1 | tee $OUT/${TAG}_fixed_cost.txt
+echo "== submission lanes" ; python tools/two_engine_probe.py 300 2>&1 | tee $OUT/${TAG}_submit_collect_lanes.txt
 echo "== launch list (only after the plain run above exited)"
 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file $OUT/${TAG}_launches_q1_bench.csv \
     python bench.py --steps 3 --warmup 3 --no-workloads --no-scaling-run --no-cpu-baseline > /dev/null 2>&1
