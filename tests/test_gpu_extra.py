@@ -438,6 +438,27 @@ def test_bond_curve_submit_collect(engine, hw):
     other = engine.bond_curve(hw.Rng(99, 4096), timing=False)
     again = engine.bond_curve_collect(slot=1)
     assert (again["P"] == want[0]["P"]).all() and not (other["P"][1:] == want[0]["P"][1:]).all()
+    # a different model per call (one curve per sigma bump, src/3:449-482): every lane follows the caller's set_model
+    base = engine.params
+    sigmas = [0.08, 0.09, 0.1, 0.11, 0.12]
+    try:
+        blocking = []
+        for sg in sigmas:
+            engine.set_model(hw.default_params(sigma=sg))
+            blocking.append(engine.bond_curve(hw.Rng(77, 6000), timing=False))
+        lanes = [None] * len(sigmas)
+        for k, sg in enumerate(sigmas):
+            if k >= slots:
+                lanes[k - slots] = engine.bond_curve_collect(slot=k % slots)
+            engine.set_model(hw.default_params(sigma=sg))
+            engine.bond_curve_submit(hw.Rng(77, 6000), slot=k % slots)
+        for k in range(max(0, len(sigmas) - slots), len(sigmas)):
+            lanes[k] = engine.bond_curve_collect(slot=k % slots)
+        for b, l in zip(blocking, lanes):
+            assert (b["P"] == l["P"]).all() and (b["f"] == l["f"]).all()
+        assert not (blocking[0]["P"][1:] == blocking[-1]["P"][1:]).any()
+    finally:
+        engine.set_model(base)
     with pytest.raises(hw.HW1FError):
         engine.bond_curve_collect(slot=2)                 # nothing submitted
     engine.bond_curve_submit(hw.Rng(1, 2048), slot=0)
