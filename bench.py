@@ -775,7 +775,10 @@ def main():
                 "blocking": {"value": path_steps_per_step / (e2e_blocking_ms * 1e-3), "ms_per_step": e2e_blocking_ms,
                              "note": "one call at a time: the host waits for every step before it issues the next"},
                 # set_model uploads ONE arena: 2 duplicated drift tables + centring + exp(-Im), 256-byte aligned pieces
-                "h2d_bytes_per_step": 2 * (((n_steps + 2) * 8 + 255) // 256 * 256) + 2 * ((n_mat * 4 + 255) // 256 * 256),
+                # (with the result slots in flight the lane that runs a step uploads it again: slot 0 is the caller's own
+                # upload, the other lanes follow it -> (2 S - 1) / S uploads per step on average over S slots)
+                "h2d_bytes_per_step": int((2 * (((n_steps + 2) * 8 + 255) // 256 * 256) + 2 * ((n_mat * 4 + 255) // 256 * 256))
+                                          * ((2 * hw._ffi.ASYNC_SLOTS - 1) / hw._ffi.ASYNC_SLOTS if world == 1 else 1)),
                 "d2h_bytes_per_step": 3 * n_mat * 4},
         "gpu_launches": int(launches),
         "clocks": clocks, "clock_check": "rejected: thermal/hw slowdown seen" if bad else "ok",

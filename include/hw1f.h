@@ -154,7 +154,8 @@ int hw1f_bond_curve(hw1f_engine* eng, hw1f_rng* rng, float* P, float* f, float* 
  * 0.580 with two submissions in one lane, 0.564 with two lanes, 0.553 with four.  Same kernels, same results bit for bit
  * as hw1f_bond_curve.  A slot must be collected before it is submitted to again; calls in different slots are not
  * ordered against each other; hw1f_engine_set_stream moves slot 0 only; hw1f_set_model with a different n_mat fails
- * while submissions are in flight; hw1f_bond_curve_ci sees slot-0 launches only. */
+ * while submissions are in flight; hw1f_bond_curve_ci refers to the last launch of slot 0 or of a blocking call (the other
+ * lanes keep their block partials to themselves). */
 #define HW1F_ASYNC_SLOTS 4
 int hw1f_bond_curve_submit(hw1f_engine* eng, hw1f_rng* rng, int32_t slot);
 int hw1f_bond_curve_collect(hw1f_engine* eng, int32_t slot, float* P, float* f, float* P_se);

@@ -1464,7 +1464,6 @@ int hw1f_bond_curve_submit(hw1f_engine* e, hw1f_rng* rng, int32_t slot)
         if (t != e) e->err = t->err;
         return st;
     }
-    if (t != e) e->ci_valid = false;   // the block partials of this launch live in the other lane
     e->slot_busy[slot] = true;
     return HW1F_OK;
 }
