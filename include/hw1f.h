@@ -150,8 +150,9 @@ int hw1f_bond_curve(hw1f_engine* eng, hw1f_rng* rng, float* P, float* f, float* 
  * engine (own stream, scratch and tables, created by the first submission to that slot; it follows every
  * hw1f_set_model / hw1f_engine_set_mode of the caller).  Walk the slots round robin and the GPU works on the next calls
  * -- jump tables, stream derivation of the first wave -- under the drain and the tail of the current one, while the host
- * reads the previous one.  Measured at 2^20 subsequences (tools/two_engine_probe.py): 0.600 ms per call blocking,
- * 0.580 with two submissions in one lane, 0.564 with two lanes, 0.553 with four.  Same kernels, same results bit for bit
+ * reads the previous one.  Measured at 2^20 subsequences (tools/two_engine_probe.py, profiles/r02_submit_collect_lanes.txt):
+ * 0.600 ms per call blocking, 0.564 / 0.558 / 0.553 with two / three / four slots in flight (0.580 when the calls in flight
+ * shared one stream, i.e. without the overlap on the GPU).  Same kernels, same results bit for bit
  * as hw1f_bond_curve.  A slot must be collected before it is submitted to again; calls in different slots are not
  * ordered against each other; hw1f_engine_set_stream moves slot 0 only; hw1f_set_model with a different n_mat fails
  * while submissions are in flight; hw1f_bond_curve_ci refers to the last launch of slot 0 or of a blocking call (the other
