@@ -467,3 +467,20 @@ def test_bond_curve_submit_collect(engine, hw):
     with pytest.raises(hw.HW1FError):
         engine.bond_curve_submit(hw.Rng(2, 2048), slot=slots)
     engine.bond_curve_collect(slot=0)
+    # a fresh engine: the last slot first (its lane is created on demand), a model of another size is refused while a
+    # submission is out, and destroying the engine with submissions in flight is clean
+    e2 = hw.Engine(device=0)
+    try:
+        e2.set_mode(engine.mode)
+        e2.bond_curve_submit(hw.Rng(5, 3000), slot=slots - 1)
+        with pytest.raises(hw.HW1FError):
+            e2.set_model(hw.default_params(n_steps=1000, n_mat=51))
+        got3 = e2.bond_curve_collect(slot=slots - 1)
+        assert (got3["P"] == engine.bond_curve(hw.Rng(5, 3000), timing=False)["P"]).all()
+        e2.set_model(hw.default_params(n_steps=1000, n_mat=51))      # nothing in flight any more
+        e2.bond_curve_submit(hw.Rng(6, 3000), slot=1)
+        e2.bond_curve_submit(hw.Rng(7, 3000), slot=0)
+        c51 = e2.bond_curve_collect(slot=1)
+        assert c51["P"].shape == (51,) and abs(c51["P"][0] - 1.0) < 2e-7
+    finally:
+        e2.close()                                                   # slot 0 still in flight
