@@ -10,7 +10,8 @@
 //   * the XORWOW state of a subsequence is re-derived in the prologue:
 //        v = J^(hi*L) * ( J^lo * T^offset * v0(seed) ),   path = hi*L + lo,
 //     the bracket comes from the per-launch table U (prep_lo_kernel), J^(hi*L) is applied as
-//     40 nibble look-ups into a 12.8 KB window table staged in shared memory.
+//     window look-ups into a table staged in shared memory: 32 five-bit windows (20.5 KB, decomposed curve / ZBC /
+//     fused kernels) or 40 four-bit windows (12.8 KB, the others); hw1f_device.cuh.
 //   * time loop in registers, drift table in shared memory as duplicated float2 (one LDS.128
 //     feeds two steps of both lanes), Box-Muller phase static (no flag, no branch).
 //   * reductions: warp shuffle tree -> shared -> one double partial row per block -> tail_kernel
