@@ -708,7 +708,7 @@ def main():
         # static: committed timing ablations of the decomposed step (not measured in this run)
         "ablation": read_json(os.path.join(ROOT, "profiles", "r02_ablation.json")) if args.mode == "decomposed" else None,
         "kernel": ("fast_kernel<1,0,0>" if args.mode == "decomposed" else "bond_curve_kernel<1>") +
-                  " (prep_lo_kernel + reduce_curve_kernel included in the time)",
+                  " (prep_lo_kernel and tail_kernel included in the time)",
         "other_mode": {"mode": other, "ms_per_step": other_ms,
                        "value": path_steps_per_step / world / (other_ms * 1e-3),
                        "issue_frac": path_steps_per_step / world / (other_ms * 1e-3) * ALGO[other]["issue"] / issue_peak},
