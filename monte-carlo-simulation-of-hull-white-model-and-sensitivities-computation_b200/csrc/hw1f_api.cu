@@ -553,6 +553,25 @@ PlanJob plan_job_dev(hw1f_engine* e, const ScenDev* sc, int n_scen, float S1, fl
     return job;
 }
 
+// Save points a recalibration-curve pass (fast_kernel DUMP) has to evaluate: the pricing behind it interpolates P and f
+// at S1 and P at S2 on the grid (compute_plan: data[idx], data[idx + 1]; f[m] differences P[m -+ 1]) and reads P at the
+// last maturity (P(0,S2) of run_zbc_price, src/3:140-157).  Two windows of six grid points from idx - 2 on; the kernel
+// adds the last two grid points.  Bit 31 marks the code (lead >= 0: every save point).
+int keep_code(const hw1f_engine* e, float S1, float S2)
+{
+    const int n = e->p.n_mat;
+    const float inv = 1.0f / e->spacing;
+    auto first = [&](float T) {
+        const float prod = T * inv;
+        int idx = (prod >= (float)n) ? n : (int)prod;
+        idx -= 2;
+        if (idx < 0) idx = 0;
+        if (idx > 1023) idx = 1023;
+        return (unsigned)idx;
+    };
+    return (int)(first(S1) | (first(S2) << 10) | 0x80000000u);
+}
+
 int launch_plan_job(hw1f_engine* e, const PlanJob& job)
 {
     plan_job_kernel<<<1, 32, 0, e->stream>>>(model_dev(e), job);
@@ -716,7 +735,7 @@ int launch_tail(hw1f_engine* e, const Launch& L, uint64_t n_local, int nq, int n
 // dump_steps > 0 (decomposed mode, two scenarios, dump_steps on a save point): the kernel also stores the noise
 // state of every subsequence at that step into e->d_state (see fast_kernel DUMP)
 int launch_curve(hw1f_engine* e, const Launch& L, const ScenDev* sc, int nscen, double* d_moments, int dump_steps = 0,
-                 const Finish& fin = Finish())
+                 const Finish& fin = Finish(), int keep = 0)
 {
     const int nm = e->p.n_mat, nq = nscen * 2 * nm;
     HW_CUDA(e, e->d_partials.ensure((size_t)L.n_runs * L.grid_x * nq));
@@ -746,7 +765,7 @@ int launch_curve(hw1f_engine* e, const Launch& L, const ScenDev* sc, int nscen, 
             HW_CUDA(e, e->d_state.ensure((size_t)L.n_runs * L.g.n_chunks * kChunk));
             HW_TRY(set_smem(e, (fast_kernel<2, 0, 0, 1>), smem));
             HW_CUDA(e, launch_k(fast_kernel<2, 0, 0, 1>, grid, kThreads, smem, e->stream, true, L.g, L.seeds, md, c0, c1, c0,
-                                c0, c0, tg, e->d_plans.p, dump_steps, 0, 0.f, e->d_partials.p, e->d_state.p));
+                                c0, c0, tg, e->d_plans.p, dump_steps, keep, 0.f, e->d_partials.p, e->d_state.p));
         } else {
             HW_TRY(set_smem(e, fast_kernel<2, 0, 0>, smem));
             HW_CUDA(e, launch_k(fast_kernel<2, 0, 0>, grid, kThreads, smem, e->stream, true, L.g, L.seeds, md, c0, c1, c0, c0,
@@ -1817,7 +1836,7 @@ static int recal_run(hw1f_engine* e, hw1f_rng* rng, float S1, float S2, float K,
     fc.dev_curve = e->d_mkt.p;
     fc.host_curve = res_curve(e, res_area);
     fc.plan = plan_job_dev(e, sc, 2, S1, S2);
-    HW_TRY(launch_curve(e, L, sc, 2, e->d_moments.p, one_pass ? n : 0, fc));
+    HW_TRY(launch_curve(e, L, sc, 2, e->d_moments.p, one_pass ? n : 0, fc, one_pass ? keep_code(e, S1, S2) : 0));
     Finish fz;
     fz.host_mom = res_mom(e, res_area);
     if (one_pass) HW_TRY(launch_zbc_from_state(e, L, sc, n, K, d_moments, fz));
@@ -1943,7 +1962,8 @@ int hw1f_vega(hw1f_engine* e, hw1f_rng* rng, float S1, float S2, float K, const 
         const size_t smem = smem_fast(e, 2, 3, 1, 1);
         HW_TRY(set_smem(e, (fast_kernel<2, 3, 1, 1, 1>), smem));
         HW_CUDA(e, launch_k(fast_kernel<2, 3, 1, 1, 1>, dim3(L.grid_x), kThreads, smem, e->stream, true, L.g, L.seeds,
-                            model_dev(e), c0, c1, zb, zm, zp, tg, e->d_plans.p, n, 0, K, e->d_partials.p, e->d_state.p));
+                            model_dev(e), c0, c1, zb, zm, zp, tg, e->d_plans.p, n, keep_code(e, S1, S2), K, e->d_partials.p,
+                            e->d_state.p));
         HW_TRY(check_launch(e, "fast_kernel<q3 sequence>"));
         Finish fc;
         fc.host_mom = res_mom(e, 0);          // [4 nm curve sums][5 unused][pathwise 3][FD- 5][FD+ 5]

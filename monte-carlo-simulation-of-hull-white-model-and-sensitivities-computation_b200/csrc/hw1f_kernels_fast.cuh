@@ -139,7 +139,13 @@ __device__ __forceinline__ void fast_zbc_mom5(float2 h, float2 q, const FastScen
 // DUMP  : 1 = also store the noise state (h, q) of every subsequence at step n_steps_S1 (a save point) to
 //         dump[run][chunk * kChunk + {tid, tid + kThreads}] as float4 (h_A, q_A, h_B, q_B) halves, so that payoffs
 //         whose constants depend on THIS pass's curve (recalibrated FD, src/3:484-525) are evaluated afterwards
-//         by zbc_from_state_kernel without simulating the same normals again
+//         by zbc_from_state_kernel without simulating the same normals again.  The curves of such a pass are read by
+//         that pricing only -- P at the grid points around S1 and S2 and at the last maturity, f around S1 -- so `lead`
+//         (unused by curve kernels, which start on a pair boundary) carries the two windows of maturities whose save
+//         points are evaluated (keep_code(): a0 | b0 << 10 | 1 << 31, windows [a0, a0 + 6) and [b0, b0 + 6), plus the
+//         last two grid points); the other sums stay zero = the noise-free curve after un-centring.  88 of 100 save
+//         points and their warp reductions drop out of the recalibration pass: Q3 sequence 1.252 -> 1.178 ms, recalibrated FD
+//         0.703 -> 0.620 ms (profiles/r02_ab_window_width.txt), every price bit for bit the same
 // partials[run][block][NCUR*2*n_mat + NZBC*5 + (PW ? 3 : 0)] doubles; the S1 block is laid out as
 // [ZBC scenario 0 (5)] [pathwise (3)] [ZBC scenarios 1.. (5 each)]  == the hw1f_fused* ABI order
 template <int NZBC, int PW>
@@ -255,6 +261,12 @@ fast_kernel(StreamGeom g, SeedArgs seeds, ModelDev md, FastScen cs0, FastScen cs
             }
         };
 
+        // DUMP passes: only the save points the pricing behind this pass reads (block-uniform test)
+        const unsigned keep_a = (unsigned)lead & 1023u, keep_b = ((unsigned)lead >> 10) & 1023u;
+        const bool keep_all = lead >= 0;
+        auto keep_m = [&](int m) {
+            return keep_all || (unsigned)(m - (int)keep_a) < 6u || (unsigned)(m - (int)keep_b) < 6u || m >= n_mat - 2;
+        };
         bool big = false;   // a lane of this warp is near the validity limit of the save-point polynomial
         auto save_curve = [&](int m) {
 #pragma unroll
@@ -413,7 +425,7 @@ fast_kernel(StreamGeom g, SeedArgs seeds, ModelDev md, FastScen cs0, FastScen cs
 #else
                 advance(half);
 #endif
-                save_curve(m);
+                if (!DUMP || keep_m(m)) save_curve(m);
                 if (!SEQ && kS1 > 0 && m == m_S1) eval_S1(true, true);
                 if (DUMP && m == m_S1) {
                     float2* d = dump + ((size_t)run * g.n_chunks + chunk) * kChunk + tid;
