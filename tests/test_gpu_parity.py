@@ -201,6 +201,43 @@ def test_vega_fd_recalibrated_vs_oracle(engine, hw, oracle, n_steps):
     assert got["price_plus_recal"] == pytest.approx(prices[1], rel=5e-5)
 
 
+@pytest.mark.parametrize("over,S1,S2", [
+    (dict(), 2.0, 7.0),                                   # windows in the middle of the grid
+    (dict(), 0.1, 0.3),                                   # left edge: the S1 window starts at grid point 0
+    (dict(), 9.0, 10.0),                                  # both windows at the right edge
+    (dict(n_steps=240, n_mat=13, T_final=2.4), 1.0, 2.0),  # a 13-point grid: the windows cover most of it
+])
+def test_vega_fd_recalibrated_sparse_save_points(engine, hw, over, S1, S2):
+    """the one-pass recalibration evaluates only the save points its pricing reads (two windows around S1 and S2 and
+    the last maturity, fast_kernel DUMP): same prices as full curves from engines whose model carries the bumped sigma"""
+    eps, n = 0.001, 1 << 13
+    e1 = hw.Engine(device=0, params=hw.default_params(**over))
+    e1.set_mode(engine.mode)
+    try:
+        ns = e1.steps_to(S1)
+        if ns % e1.constants.save_stride:
+            ns -= ns % e1.constants.save_stride            # on the maturity grid: the one-pass route
+        c0 = e1.bond_curve(hw.Rng(9, n))
+        nm = e1.n_mat
+        K = float(np.float32(0.9) * c0["P"][int(round(S2 / e1.constants.mat_spacing))] /
+                  c0["P"][int(round(S1 / e1.constants.mat_spacing))])
+        got = e1.vega_fd_recalibrated(hw.Rng(SEED, n).seek(1000), eps=eps, S1=S1, S2=S2, K=K, n_steps_S1=ns)
+        prices = []
+        for sgn in (-1.0, 1.0):
+            sg = float(np.float32(e1.params.sigma) + np.float32(sgn * eps))
+            e2 = hw.Engine(device=0, params=hw.default_params(sigma=sg, **over))
+            e2.set_mode(engine.mode)
+            c = e2.bond_curve(hw.Rng(SEED, n).seek(1000))
+            z = e2.zbc_cv(hw.Rng(SEED, n).seek(1000), c["P"], c["f"], S1=S1, S2=S2, K=K, n_steps_S1=ns)
+            prices.append(z["price_cv"])
+            e2.close()
+        assert nm == len(c["P"])
+        assert got["price_minus_recal"] == pytest.approx(prices[0], rel=3e-6)
+        assert got["price_plus_recal"] == pytest.approx(prices[1], rel=3e-6)
+    finally:
+        e1.close()
+
+
 def test_vega_fd_recalibrated_equals_bumped_engines(engine, hw):
     """recompute_market_data + run_zbc_price at sigma -/+ eps (src/3:449-525) composed from the public single-scenario
     calls on engines whose MODEL carries the bumped sigma (the base drift does not depend on sigma): the fused
