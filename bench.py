@@ -647,6 +647,12 @@ def main():
     workloads = None
     if world == 1 and not args.no_workloads:
         workloads = measure_workloads(eng, hw, n_paths, mkt)
+        q1 = workloads.get("q1_bond_curve")
+        if isinstance(q1, dict) and q1.get("reference_ms"):
+            # the same workload through the submission lanes (the e2e region above): model upload, simulation and the
+            # host read of P, f, P_se every call, four result slots in flight
+            q1["engine_ms_four_slots_in_flight"] = e2e_ms
+            q1["ratio_four_slots_in_flight"] = q1["reference_ms"] / e2e_ms
 
     # ---- BASELINE.json configs[4]: the 2^30 fused strong-scaling run on every N ----
     scal = None
