@@ -239,7 +239,10 @@ int hw1f_vega_fd(hw1f_engine* eng, hw1f_rng* rng, float S1, float S2, float K,
                  const float* P_mkt, const float* f_mkt, float eps, int32_t n_steps_S1,
                  hw1f_vega_result* out);
 /* recompute_market_data at sigma -/+ eps (both curves in one launch) then the two prices; the
- * handle is left where the reference leaves its state array (advanced by n_steps_S1). */
+ * handle is left where the reference leaves its state array (advanced by n_steps_S1).  The two
+ * recalibrated curves are internal to the call (src/3:449-525 keeps them in device buffers that only
+ * run_zbc_price reads): with S1 on the maturity grid the pass evaluates only the save points that
+ * pricing interpolates on -- grid points around S1 and S2 and the last maturity -- same prices bit for bit. */
 int hw1f_vega_fd_recalibrated(hw1f_engine* eng, hw1f_rng* rng, float S1, float S2, float K,
                               float eps, int32_t n_steps_S1, hw1f_vega_result* out);
 /* the whole q3 sequence with the reference's draw windows: pathwise on normals [0,n),
